@@ -1,0 +1,367 @@
+// attn.cu -- area 4: decode attention over a per-token-quantized KV cache (sm_100a).
+//
+// The reference dequantizes EVERY stored token, concatenates, wraps the result in a DynamicCache and
+// lets transformers run softmax(q k^T / sqrt(D)) v (src/benchmarking/benchmarker.py:470-477,
+// src/quantization/ops.py:213-269, :345-355).  Here the cache is read once, as codes: INT8 or packed
+// INT4 K/V are dequantized in registers (code * scale[t]) inside a split-K GEMV with an online
+// softmax.  No tensor cores: at decode the query is one token, so per KV head this is a
+// [G x D] . [D x T] product with G = Hq/H <= 8 rows -- bandwidth-bound streaming, not a dense GEMM.
+//
+// Grid (n_splits, H, B), 128 threads.  Per tile of 128 tokens:
+//   K phase  : a lane owns 16 consecutive d of one token (16 B of INT8 / 8 B of INT4); partial dot
+//              products are reduced over the D/16 lanes of the row by shuffles.
+//   softmax  : per query head, tile max / running max / exp2 / running sum in one warp.
+//   V phase  : a lane owns a fixed slice of 32/G consecutive d for every token of its row group and
+//              accumulates G x (32/G) fp32 partial outputs; row groups are summed through shared
+//              memory once per split.
+// Partials (m, l, acc[D]) per (b, hq, split) go to the workspace; a second kernel merges the splits.
+#include <cmath>
+
+#include "kvq_common.cuh"
+
+namespace kvq {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kTile = 128;  // tokens per tile
+
+struct AttnParams {
+    const void* q; int q_dtype;
+    const uint8_t* k; int64_t kB, kH, kT; const float* k_scale;
+    const uint8_t* v; int64_t vB, vH, vT; const float* v_scale;
+    int B, Hq, H, T;
+    float qk_scale_log2;  // sm_scale * log2(e)
+    int tokens_per_split, n_splits;
+    float* ws_acc;  // [B, Hq, n_splits, D]
+    float* ws_ml;   // [B, Hq, n_splits, 2]
+};
+
+// 4 codes of one 32-bit word -> 4 floats, exact.  INT8: flip the sign bit so the byte is code+128,
+// drop it into the mantissa of 2^23 (PRMT), subtract 2^23+128.
+__device__ __forceinline__ void int8x4_to_float(uint32_t w, float f[4]) {
+    const uint32_t x = w ^ 0x80808080u;
+    f[0] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650)) - 8388736.f;
+    f[1] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7651)) - 8388736.f;
+    f[2] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7652)) - 8388736.f;
+    f[3] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7653)) - 8388736.f;
+}
+// 8 nibbles of one 32-bit word (4 bytes; byte j = elements 2j (high nibble), 2j+1 (low)) -> 8 floats = code
+__device__ __forceinline__ void int4x8_to_float(uint32_t w, float f[8]) {
+    const uint32_t lo = w & 0x0f0f0f0fu, hi = (w >> 4) & 0x0f0f0f0fu;
+    f[0] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650)) - 8388616.f;
+    f[1] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650)) - 8388616.f;
+    f[2] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7651)) - 8388616.f;
+    f[3] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7651)) - 8388616.f;
+    f[4] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7652)) - 8388616.f;
+    f[5] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7652)) - 8388616.f;
+    f[6] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7653)) - 8388616.f;
+    f[7] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7653)) - 8388616.f;
+}
+
+// N consecutive codes starting at a byte pointer, as floats.  N*BITS/8 bytes, naturally aligned.
+template <int BITS, int N> struct CodeVec {
+    static constexpr int kBytes = N * BITS / 8;
+    static constexpr int kWords = kBytes >= 4 ? kBytes / 4 : 1;
+    uint32_t w[kWords];
+    __device__ __forceinline__ void load(const uint8_t* p) {
+        if (kBytes == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
+        else if (kBytes == 4) w[0] = *reinterpret_cast<const uint32_t*>(p);
+        else if (kBytes == 8) { const uint2 t = ld_stream8(p); w[0] = t.x; w[1] = t.y; }
+        else {
+#pragma unroll
+            for (int i = 0; i < kBytes / 16; ++i) {
+                const uint4 t = ld_stream(p + 16 * i);
+                w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+            }
+        }
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) w[i] = BITS == 8 ? 0u : 0x88888888u;
+    }
+    __device__ __forceinline__ void to_float(float f[N]) const {
+        if (BITS == 8) {
+            if (N >= 4) {
+#pragma unroll
+                for (int i = 0; i < N / 4; ++i) int8x4_to_float(w[i], f + 4 * i);
+            }
+        } else {
+            if (N >= 8) {
+#pragma unroll
+                for (int i = 0; i < N / 8; ++i) int4x8_to_float(w[i], f + 8 * i);
+            } else {  // N == 4: two bytes
+                float t[8];
+                int4x8_to_float(w[0], t);
+#pragma unroll
+                for (int i = 0; i < N; ++i) f[i] = t[i];
+            }
+        }
+    }
+};
+
+template <int KBITS, int VBITS, int G, int D>
+__global__ void __launch_bounds__(kThreads) decode_attn_split_kernel(AttnParams P) {
+    constexpr int LPR = D / 16;            // K: lanes per row
+    constexpr int KROWS = kThreads / LPR;  // K rows per pass
+    constexpr int KPASS = kTile / KROWS;
+    constexpr int EV = 32 / G;             // V: elements per lane
+    constexpr int LPRV = D / EV;
+    constexpr int VROWS = kThreads / LPRV;
+    constexpr int VPASS = kTile / VROWS;
+    constexpr bool kQRegs = G <= 2;
+    static_assert(G == 1 || G == 2 || G == 4 || G == 8, "G");
+    static_assert(D == 64 || D == 128, "D");
+
+    __shared__ float q_s[G][D];
+    __shared__ float p_s[G][kTile];
+    __shared__ float alpha_s[G], m_s[G], l_s[G];
+    __shared__ float red_s[kThreads * 32];
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t_begin = split * P.tokens_per_split;
+    const int t_end = min(P.T, t_begin + P.tokens_per_split);
+
+    // q (G heads of this kv head), pre-scaled into the log2 domain
+    for (int i = tid; i < G * D; i += kThreads) {
+        const int g = i / D, d = i - g * D;
+        const int64_t qi = ((int64_t)b * P.Hq + (int64_t)h * G + g) * D + d;
+        q_s[g][d] = load_scale(P.q, P.q_dtype, qi) * P.qk_scale_log2;
+    }
+    if (tid < G) { m_s[tid] = -INFINITY; l_s[tid] = 0.f; alpha_s[tid] = 0.f; }
+    __syncthreads();
+
+    const int kc = tid % LPR, kr = tid / LPR;
+    const int vc = tid % LPRV, vr = tid / LPRV;
+    float qr[kQRegs ? G : 1][16];
+    if (kQRegs) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) qr[g][e] = q_s[g][kc * 16 + e];
+    }
+    float acc[G][EV];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < EV; ++e) acc[g][e] = 0.f;
+
+    const uint8_t* kbase = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH + (int64_t)kc * (16 * KBITS / 8);
+    const uint8_t* vbase = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH + (int64_t)vc * (EV * VBITS / 8);
+
+    for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
+        // ---- issue all loads of the tile (K then V) before any math
+        CodeVec<KBITS, 16> kv[KPASS];
+        float ks[KPASS];
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) {
+            const int t = t0 + ps * KROWS + kr;
+            if (t < t_end) { kv[ps].load(kbase + (int64_t)t * P.kT); ks[ps] = P.k_scale[t]; }
+            else { kv[ps].zero(); ks[ps] = 0.f; }
+        }
+        CodeVec<VBITS, EV> vv[VPASS];
+#pragma unroll
+        for (int ps = 0; ps < VPASS; ++ps) {
+            const int t = t0 + ps * VROWS + vr;
+            if (t < t_end) vv[ps].load(vbase + (int64_t)t * P.vT); else vv[ps].zero();
+        }
+        // ---- K phase: scores (log2 domain) into p_s
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) {
+            float f[16];
+            kv[ps].to_float(f);
+            const int row = ps * KROWS + kr;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float d = 0.f;
+                if (kQRegs) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) d = fmaf(qr[g][e], f[e], d);
+                } else {
+                    const float4* qp = reinterpret_cast<const float4*>(&q_s[g][kc * 16]);
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 qq = qp[e4];
+                        d = fmaf(qq.x, f[4 * e4], d); d = fmaf(qq.y, f[4 * e4 + 1], d);
+                        d = fmaf(qq.z, f[4 * e4 + 2], d); d = fmaf(qq.w, f[4 * e4 + 3], d);
+                    }
+                }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (kc == 0) p_s[g][row] = (t0 + row < t_end) ? d * ks[ps] : -INFINITY;
+            }
+        }
+        __syncthreads();
+        // ---- softmax bookkeeping: warp w owns heads w, w+4
+        for (int g = warp; g < G; g += kThreads / 32) {
+            float s[kTile / 32], mt = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kTile / 32; ++i) { s[i] = p_s[g][lane + 32 * i]; mt = fmaxf(mt, s[i]); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+            const float m_old = m_s[g], m_new = fmaxf(m_old, mt);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < kTile / 32; ++i) {
+                const int t = t0 + lane + 32 * i;
+                const float p = (t < t_end) ? exp2f(s[i] - m_new) : 0.f;
+                sum += p;
+                p_s[g][lane + 32 * i] = (t < t_end) ? p * P.v_scale[t] : 0.f;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            __syncwarp();
+            if (lane == 0) {
+                const float a = (m_old == -INFINITY) ? 0.f : exp2f(m_old - m_new);
+                alpha_s[g] = a; m_s[g] = m_new; l_s[g] = l_s[g] * a + sum;
+            }
+        }
+        __syncthreads();
+        // ---- V phase
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float a = alpha_s[g];
+#pragma unroll
+            for (int e = 0; e < EV; ++e) acc[g][e] *= a;
+        }
+#pragma unroll
+        for (int ps = 0; ps < VPASS; ++ps) {
+            float f[EV];
+            vv[ps].to_float(f);
+            const int row = ps * VROWS + vr;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float w = p_s[g][row];
+#pragma unroll
+                for (int e = 0; e < EV; ++e) acc[g][e] = fmaf(w, f[e], acc[g][e]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- sum the VROWS row groups through shared memory; write the split's partial
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < EV; ++e) red_s[(vr * G + g) * D + vc * EV + e] = acc[g][e];
+    __syncthreads();
+    for (int o = tid; o < G * D; o += kThreads) {
+        float s = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < VROWS; ++r) s += red_s[r * G * D + o];
+        const int g = o / D, d = o - g * D;
+        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
+        P.ws_acc[(hq * P.n_splits + split) * D + d] = s;
+    }
+    if (tid < G) {
+        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + tid;
+        P.ws_ml[(hq * P.n_splits + split) * 2] = m_s[tid];
+        P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = l_s[tid];
+    }
+}
+
+template <int ODT>
+__global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
+                                         void* __restrict__ out) {
+    const int64_t hq = blockIdx.x;
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    float M = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws_ml[(hq * n_splits + s) * 2]);
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < n_splits; ++s) {
+        const float m = ws_ml[(hq * n_splits + s) * 2];
+        const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+        num = fmaf(ws_acc[(hq * n_splits + s) * D + d], w, num);
+        den = fmaf(ws_ml[(hq * n_splits + s) * 2 + 1], w, den);
+    }
+    store_scalar<ODT>(out, hq * D + d, num / den);
+}
+
+template <int KBITS, int VBITS, int G>
+int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P) {
+    if (D == 128) decode_attn_split_kernel<KBITS, VBITS, G, 128><<<grid, kThreads, 0, st>>>(P);
+    else decode_attn_split_kernel<KBITS, VBITS, G, 64><<<grid, kThreads, 0, st>>>(P);
+    return KVQ_OK;
+}
+template <int KBITS, int VBITS>
+int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P) {
+    switch (G) {
+        case 1: return launch_split<KBITS, VBITS, 1>(D, grid, st, P);
+        case 2: return launch_split<KBITS, VBITS, 2>(D, grid, st, P);
+        case 4: return launch_split<KBITS, VBITS, 4>(D, grid, st, P);
+        case 8: return launch_split<KBITS, VBITS, 8>(D, grid, st, P);
+    }
+    return fail(KVQ_ERR_UNSUPPORTED, "decode_attn: Hq/H must be 1, 2, 4 or 8 (got %d)", G);
+}
+
+int choose_splits(int64_t B, int64_t H, int64_t T) {
+    const int64_t target = 4LL * sm_count();
+    int64_t n = (target + B * H - 1) / (B * H);
+    const int64_t max_n = (T + 255) / 256;
+    if (n > max_n) n = max_n;
+    if (n < 1) n = 1;
+    return (int)n;
+}
+
+}  // namespace
+}  // namespace kvq
+
+using namespace kvq;
+
+extern "C" int64_t kvq_decode_attn_workspace_bytes(int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, int* n_splits) {
+    if (B <= 0 || Hq <= 0 || H <= 0 || T <= 0 || D <= 0) { if (n_splits) *n_splits = 1; return 0; }
+    const int n = choose_splits(B, H, T);
+    if (n_splits) *n_splits = n;
+    return B * Hq * n * (D + 2) * (int64_t)sizeof(float);
+}
+
+extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                               const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                               const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                               void* out, int out_dtype, void* workspace, int n_splits, kvq_stream_t stream) {
+    KVQ_REQUIRE(q && k_codes && v_codes && k_scale && v_scale && out && workspace, "null pointer");
+    KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
+    KVQ_REQUIRE((k_bits == 8 || k_bits == 4) && (v_bits == 8 || v_bits == 4), "k_bits / v_bits must be 8 or 4");
+    KVQ_REQUIRE(D == 64 || D == 128, "decode_attn: head_dim must be 64 or 128 (got %lld)", (long long)D);
+    KVQ_REQUIRE(B >= 1 && H >= 1 && Hq >= 1 && T >= 1 && T <= 0x7fffffff && B <= 65535 && H <= 65535, "bad shape");
+    KVQ_REQUIRE(Hq % H == 0, "Hq must be a multiple of H");
+    KVQ_REQUIRE(n_splits >= 1, "n_splits must be >= 1");
+    const int64_t kw = k_bits == 8 ? D : D / 2, vw = v_bits == 8 ? D : D / 2;
+    const Stride3 ks = make_stride3(k_stride3, H, T, kw), vs = make_stride3(v_stride3, H, T, vw);
+    auto al = [](const void* p, const Stride3& s, int a) {
+        return reinterpret_cast<uintptr_t>(p) % a == 0 && s.sB % a == 0 && s.sH % a == 0 && s.sT % a == 0;
+    };
+    KVQ_REQUIRE(al(k_codes, ks, 16) && al(v_codes, vs, 16), "decode_attn: code tensors must be 16-byte aligned with 16-byte-multiple strides");
+    cudaStream_t st = (cudaStream_t)stream;
+    AttnParams P{};
+    P.q = q; P.q_dtype = q_dtype;
+    P.k = (const uint8_t*)k_codes; P.kB = ks.sB; P.kH = ks.sH; P.kT = ks.sT; P.k_scale = k_scale;
+    P.v = (const uint8_t*)v_codes; P.vB = vs.sB; P.vH = vs.sH; P.vT = vs.sT; P.v_scale = v_scale;
+    P.B = (int)B; P.Hq = (int)Hq; P.H = (int)H; P.T = (int)T;
+    P.qk_scale_log2 = sm_scale * 1.4426950408889634f;
+    int64_t tps = (T + n_splits - 1) / n_splits;
+    tps = (tps + kTile - 1) / kTile * kTile;
+    P.tokens_per_split = (int)tps;
+    n_splits = (int)((T + tps - 1) / tps);  // splits that actually contain tokens
+    P.n_splits = n_splits;
+    P.ws_acc = (float*)workspace;
+    P.ws_ml = P.ws_acc + B * Hq * (int64_t)n_splits * D;
+    const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
+    const int G = (int)(Hq / H);
+    int rc;
+    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P);
+    else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P);
+    else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P);
+    else rc = launch_g<4, 8>(G, (int)D, grid, st, P);
+    if (rc != KVQ_OK) return rc;
+    rc = check_launch("decode_attn_split");
+    if (rc != KVQ_OK) return rc;
+    const unsigned mt = (unsigned)D;
+    switch (out_dtype) {
+        case KVQ_F32: decode_attn_merge_kernel<KVQ_F32><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        case KVQ_F16: decode_attn_merge_kernel<KVQ_F16><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        default: decode_attn_merge_kernel<KVQ_BF16><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+    }
+    return check_launch("decode_attn_merge");
+}

@@ -1,0 +1,152 @@
+"""ctypes binding of libkvq_sm100.so (C ABI: include/kvq.h).
+
+There is no CPU path and no fallback: if the shared library is missing, or a tensor is not on a CUDA
+device, the call raises.  torch is used for device memory and streams only; every kernel launch goes
+through the C ABI with raw pointers.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("KVQ_LIB", os.path.join(_HERE, "libkvq_sm100.so"))
+
+F32, F16, BF16 = 0, 1, 2
+PER_TENSOR, PER_TOKEN = 0, 1
+SLIDING, PREFIX_WINDOW, STRIDED, BLOCK, BUDGET = 0, 1, 2, 3, 4
+
+DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+KVQ_OK, KVQ_ERR_INVALID, KVQ_ERR_CUDA, KVQ_ERR_UNSUPPORTED, KVQ_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+
+c_i64, c_int, c_f, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+I64x4 = c_i64 * 4
+I64x3 = c_i64 * 3
+
+
+class EvictPlan(ctypes.Structure):
+    """struct kvq_evict_plan (include/kvq.h)."""
+
+    _fields_ = [
+        ("strategy", ctypes.c_int32), ("identity", ctypes.c_int32), ("T", c_i64), ("n_prefix", c_i64),
+        ("n_old", c_i64), ("old_start", c_i64), ("tail_start", c_i64), ("n_tail", c_i64), ("n_total", c_i64),
+        ("stride", c_i64), ("keep", c_i64), ("budget", c_i64), ("needs_table", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+# every symbol include/kvq.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "kvq_version": (c_int, []),
+    "kvq_last_error": (ctypes.c_char_p, []),
+    "kvq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "kvq_absmax": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_vp, c_int, c_vp]),
+    "kvq_quant_int8": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kvq_quant_int4_pack": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kvq_quant_per_token_fused": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "kvq_dequant_int8": (c_int, [c_vp, I64x4, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
+    "kvq_dequant_int4_unpack": (c_int, [c_vp, I64x4, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
+    "kvq_evict_plan_make": (c_int, [c_int] + [c_i64] * 7 + [ctypes.POINTER(EvictPlan)]),
+    "kvq_evict_indices_host": (c_int, [ctypes.POINTER(EvictPlan), c_vp]),
+    "kvq_evict_indices_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),
+    "kvq_evict_gather": (c_int, [c_vp, c_int, I64x4, I64x4, ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp, c_vp]),
+    "kvq_paged_append": (c_int, [c_vp, c_int, I64x4, I64x4, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "kvq_paged_gather": (c_int, [c_vp, c_int, I64x4, c_vp, c_i64, c_vp, c_vp]),
+    "kvq_chunk_mean": (c_int, [c_vp, c_int, I64x4, I64x4, c_i64, c_i64, c_vp, c_vp]),
+    "kvq_decode_attn_workspace_bytes": (c_i64, [c_i64] * 5 + [ctypes.POINTER(c_int)]),
+    "kvq_decode_attn": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
+                        + [c_f, c_vp, c_int, c_vp, c_int, c_vp]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+_lock = threading.Lock()
+
+# launches made through the C ABI since import (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def lib() -> ctypes.CDLL:
+    """Load libkvq_sm100.so once (thread-safe; the reference's lazy singleton had no lock,
+    src/cuda/extensions.py:138-147).  Raises if the library is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: build it with `make -C efficient-llm-inference_b200/csrc` "
+                        "(or __graft_entry__.build()).  kvq_b200 has no CPU or torch fallback.")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().kvq_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    """Non-zero status -> RuntimeError (the reference raises RuntimeError through TORCH_CHECK)."""
+    if rc != KVQ_OK:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
+
+
+def count_launch(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "kvq_b200 runs on CUDA (sm_100a) tensors only; got a tensor on "
+                f"'{t.device}'.  There is no CPU fallback by design.")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return DTYPE_CODE[dt]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {dt}: expected float32, float16 or bfloat16") from None
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def as4d(x: torch.Tensor) -> torch.Tensor:
+    """View any tensor as [B,H,T,D] without copying when possible (last dim stays last)."""
+    if x.dim() == 4:
+        return x
+    if x.dim() == 0:
+        return x.reshape(1, 1, 1, 1)
+    if x.dim() < 4:
+        return x.reshape((1,) * (4 - x.dim()) + tuple(x.shape))
+    return x.reshape(-1, *x.shape[-3:])  # copies only if the leading dims cannot be merged
+
+
+def shape_stride(x4: torch.Tensor) -> Tuple[ctypes.Array, ctypes.Array]:
+    return I64x4(*x4.shape), I64x4(*x4.stride())
+
+
+def stride3(t4: torch.Tensor) -> ctypes.Array:
+    """{sB,sH,sT} of a code/output tensor whose last dim must be contiguous."""
+    if t4.size(-1) > 1 and t4.stride(-1) != 1:
+        raise RuntimeError("code / output tensors need a contiguous last dimension")
+    return I64x3(*t4.stride()[:3])
+
+
+def device_guard(t: torch.Tensor):
+    return torch.cuda.device(t.device)

@@ -1,0 +1,57 @@
+"""Fused dequantize + decode attention over a quantized KV cache (csrc/attn.cu).
+
+Not a function of the reference: there, every decode step dequantizes the whole cache, concatenates it,
+wraps it in a DynamicCache and lets transformers compute softmax(q k^T / sqrt(D)) v
+(/root/reference/src/benchmarking/benchmarker.py:470-477, src/quantization/ops.py:213-269).  This op
+replaces that round trip for the cached tokens: codes are read once and dequantized in registers.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+@torch.no_grad()
+def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales: torch.Tensor, k_bits: int,
+                               v_codes: torch.Tensor, v_scales: torch.Tensor, v_bits: int,
+                               sm_scale: Optional[float] = None, out_dtype: Optional[torch.dtype] = None,
+                               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b,hq] = softmax_t(q[b,hq] . K[b,hq//G,t] * sm_scale) @ V[b,hq//G]  with K/V = codes * scale[t].
+
+    q [B,Hq,1,D] (fp32/fp16/bf16); k_codes int8 [B,H,T,D] (k_bits 8) or uint8 [B,H,T,D/2] (k_bits 4);
+    k_scales fp32 [T]; v likewise.  G = Hq/H in {1,2,4,8}; D in {64,128}.  Returns [B,Hq,1,D].
+    """
+    L.require_cuda(q, k_codes, v_codes, k_scales, v_scales)
+    if q.dim() != 4 or q.size(2) != 1:
+        raise RuntimeError("q must be [B, Hq, 1, D] (one decode token)")
+    B, Hq, _, D = q.shape
+    H, T = k_codes.size(1), k_codes.size(2)
+    if k_codes.size(0) != B or v_codes.size(0) != B or v_codes.size(1) != H or v_codes.size(2) != T:
+        raise RuntimeError("K / V code tensors do not match q")
+    if k_scales.dtype != torch.float32 or v_scales.dtype != torch.float32:
+        raise RuntimeError("attention reads fp32 scales (QuantizedLayerKV.quantized())")
+    if k_scales.numel() != T or v_scales.numel() != T:
+        raise RuntimeError("need one scale per cached token")
+    if sm_scale is None:
+        sm_scale = float(D) ** -0.5
+    out_dtype = out_dtype or q.dtype
+    qc = q.contiguous()
+    k_scales, v_scales = k_scales.contiguous(), v_scales.contiguous()
+    out = torch.empty((B, Hq, 1, D), dtype=out_dtype, device=q.device)
+    with L.device_guard(q):
+        ns = ctypes.c_int(1)
+        nbytes = L.lib().kvq_decode_attn_workspace_bytes(B, Hq, H, T, D, ctypes.byref(ns))
+        if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+            workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=q.device)
+        L.check(L.lib().kvq_decode_attn(qc.data_ptr(), L.dtype_code(q.dtype), k_codes.data_ptr(), int(k_bits),
+                                        L.stride3(k_codes), k_scales.data_ptr(), v_codes.data_ptr(), int(v_bits),
+                                        L.stride3(v_codes), v_scales.data_ptr(), B, Hq, H, T, D, float(sm_scale),
+                                        out.data_ptr(), L.dtype_code(out_dtype), workspace.data_ptr(), ns.value,
+                                        L.stream_ptr(q.device)), "kvq_decode_attn")
+        L.count_launch(2)
+    return out

@@ -1,0 +1,379 @@
+"""INT8 / packed-INT4 KV quantization on B200: the reference's `src/quantization/ops.py` API over
+hand-written sm_100a kernels (csrc/quant.cu) reached through the C ABI (include/kvq.h).
+
+Same names, argument meaning, return arities and error behaviour as the reference
+(/root/reference/src/quantization/ops.py):
+    quantize_int8_per_tensor          :10-30     -> (int8 codes, 0-dim scale in x.dtype)
+    quantize_int4_per_tensor_packed   :33-65     -> (uint8 packed, 0-dim scale, orig_last)
+    dequantize_int8_per_tensor        :68-90
+    dequantize_int4_per_tensor_packed :93-133
+    QuantizedLayerKV                  :136-290
+    QuantizedKVCache                  :293-363
+
+Differences that are not visible in results: scales stay on the device (no float(scale) sync, reference
+:87,:117); the per-layer store is one preallocated [B,H,cap,D] code tensor plus a [cap] scale vector
+instead of Python lists of per-token tensors, so get_kv() is ONE launch per tensor instead of T launches
+and a torch.cat; init_from_prompt_past() is ONE launch per tensor instead of T.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+from ..distributed import allreduce_absmax_
+
+
+def _absmax_bits(x4: torch.Tensor, granularity: int, group=None) -> torch.Tensor:
+    """Phase 1: max|x| as fp32 bit patterns (int32 tensor; non-negative so integer max == float max)."""
+    n = x4.size(2) if granularity == L.PER_TOKEN else 1
+    bits = torch.empty(n, dtype=torch.int32, device=x4.device)
+    sh, st = L.shape_stride(x4)
+    L.check(L.lib().kvq_absmax(x4.data_ptr(), L.dtype_code(x4.dtype), sh, st, granularity, bits.data_ptr(), 0,
+                               L.stream_ptr(x4.device)), "kvq_absmax")
+    L.count_launch()
+    allreduce_absmax_(bits, group)  # head-sharded cache: the only collective on the path
+    return bits
+
+
+def _check_input(x: torch.Tensor) -> None:
+    L.require_cuda(x)
+    L.dtype_code(x.dtype)
+    if x.numel() == 0:
+        # x_fp32.abs().max() on an empty tensor raises in the reference (ops.py:27)
+        raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0")
+
+
+@torch.no_grad()
+def quantize_int8_per_tensor(x: torch.Tensor, eps: float = 1e-8, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Symmetric per-tensor INT8: q = clamp(round(x/scale), -127, 127), scale = max(max|x|/127, eps).
+
+    Two launches: absmax reduction, then quantize.  `group`: optional torch.distributed group over
+    which the tensor is head-sharded; the max is all-reduced so every shard uses the global scale.
+    """
+    _check_input(x)
+    with L.device_guard(x):
+        x4 = L.as4d(x)
+        bits = _absmax_bits(x4, L.PER_TENSOR, group)
+        q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+        scale = torch.empty((), dtype=x.dtype, device=x.device)
+        sh, st = L.shape_stride(x4)
+        L.check(L.lib().kvq_quant_int8(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(),
+                                       float(eps), q.data_ptr(), None, scale.data_ptr(), None,
+                                       L.stream_ptr(x.device)), "kvq_quant_int8")
+        L.count_launch()
+    return q, scale
+
+
+@torch.no_grad()
+def quantize_int4_per_tensor_packed(x: torch.Tensor, eps: float = 1e-8, group=None
+                                    ) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Symmetric per-tensor INT4 in [-8, 7], two codes per byte along the last dim (even index in the
+    high nibble; an odd last dim is padded with one zero code)."""
+    _check_input(x)
+    if x.dim() == 0:
+        raise IndexError("Dimension specified as -1 but tensor has no dimensions")  # q.size(-1), ops.py:53
+    with L.device_guard(x):
+        x4 = L.as4d(x)
+        bits = _absmax_bits(x4, L.PER_TENSOR, group)
+        orig_last = x.size(-1)
+        packed = torch.empty((*x.shape[:-1], (orig_last + 1) // 2), dtype=torch.uint8, device=x.device)
+        scale = torch.empty((), dtype=x.dtype, device=x.device)
+        sh, st = L.shape_stride(x4)
+        L.check(L.lib().kvq_quant_int4_pack(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(),
+                                            float(eps), packed.data_ptr(), None, scale.data_ptr(), None,
+                                            L.stream_ptr(x.device)), "kvq_quant_int4_pack")
+        L.count_launch()
+    return packed, scale, orig_last
+
+
+def _scale_arg(scale, device) -> torch.Tensor:
+    if not isinstance(scale, torch.Tensor):
+        scale = torch.tensor(float(scale), dtype=torch.float32, device=device)
+    L.require_cuda(scale)
+    if scale.dtype not in L.DTYPE_CODE:
+        scale = scale.float()
+    return scale.reshape(-1)[:1].contiguous() if scale.numel() >= 1 else scale
+
+
+@torch.no_grad()
+def dequantize_int8_per_tensor(q: torch.Tensor, scale: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """(q.float() * scale.float()).to(out_dtype) in one launch; any out_dtype in fp32/fp16/bf16
+    (the reference's kernel handled fp16 only, ops.py:85)."""
+    L.require_cuda(q)
+    if q.dtype != torch.int8:
+        raise RuntimeError("q must be int8")  # extensions.py:72
+    scale = _scale_arg(scale, q.device)
+    out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
+    if q.numel() == 0:
+        return out
+    with L.device_guard(q):
+        q4 = L.as4d(q.contiguous())
+        sh, _ = L.shape_stride(q4)
+        L.check(L.lib().kvq_dequant_int8(q4.data_ptr(), sh, None, scale.data_ptr(), L.dtype_code(scale.dtype),
+                                         L.PER_TENSOR, out.data_ptr(), L.dtype_code(out_dtype),
+                                         L.stream_ptr(q.device)), "kvq_dequant_int8")
+        L.count_launch()
+    return out
+
+
+@torch.no_grad()
+def dequantize_int4_per_tensor_packed(packed: torch.Tensor, scale: torch.Tensor, orig_last_dim: int,
+                                      out_dtype: torch.dtype) -> torch.Tensor:
+    """Unpack (high nibble -> even index), subtract 8, keep the first orig_last_dim of each row,
+    multiply by scale; one launch, each byte read once."""
+    L.require_cuda(packed)
+    if packed.dtype != torch.uint8:
+        raise RuntimeError("packed must be uint8")  # extensions.py:90
+    if packed.dim() < 1:
+        raise RuntimeError("packed must have at least 1 dim")  # extensions.py:93
+    orig_last_dim = int(orig_last_dim)
+    P = packed.size(-1)
+    if not (0 <= orig_last_dim <= 2 * P):
+        raise RuntimeError(f"orig_last_dim {orig_last_dim} does not fit {P} packed bytes per row")
+    scale = _scale_arg(scale, packed.device)
+    out = torch.empty((*packed.shape[:-1], orig_last_dim), dtype=out_dtype, device=packed.device)
+    if out.numel() == 0:
+        return out
+    with L.device_guard(packed):
+        p4 = L.as4d(packed.contiguous())
+        B, H, T = p4.shape[:3]
+        sh = L.I64x4(B, H, T, orig_last_dim)
+        s3 = L.I64x3(H * T * P, T * P, P)  # rows are P bytes apart even when orig_last < 2P
+        L.check(L.lib().kvq_dequant_int4_unpack(p4.data_ptr(), sh, s3, scale.data_ptr(), L.dtype_code(scale.dtype),
+                                                L.PER_TENSOR, out.data_ptr(), L.dtype_code(out_dtype),
+                                                L.stream_ptr(packed.device)), "kvq_dequant_int4_unpack")
+        L.count_launch()
+    return out
+
+
+class _TokenStore:
+    """Codes of one K or V stream: [B,H,cap,W] (W = D for INT8, ceil(D/2) for INT4) plus one scale per
+    token in the input dtype (what the reference returns) and the same value widened to fp32 (what the
+    fused attention kernel reads).  Capacity doubles; tokens are contiguous along dim 2."""
+
+    def __init__(self, bits: int):
+        self.bits = bits
+        self.codes: Optional[torch.Tensor] = None
+        self.scales: Optional[torch.Tensor] = None      # [cap] input dtype
+        self.scales_f32: Optional[torch.Tensor] = None  # [cap] fp32
+        self.T = 0
+        self.D = 0
+        self.n_scale_entries = 0  # how many scale tensors the reference would hold (one per append)
+
+    def _reserve(self, x: torch.Tensor, n_new: int) -> None:
+        B, H, _, D = x.shape
+        W = D if self.bits == 8 else (D + 1) // 2
+        need = self.T + n_new
+        if self.codes is None:
+            cap = max(256, 1 << (need - 1).bit_length())
+            self.D = D
+            self.codes = torch.empty((B, H, cap, W), dtype=torch.int8 if self.bits == 8 else torch.uint8, device=x.device)
+            self.scales = torch.empty(cap, dtype=x.dtype, device=x.device)
+            self.scales_f32 = torch.empty(cap, dtype=torch.float32, device=x.device)
+            return
+        if tuple(self.codes.shape[:2]) != (B, H) or self.D != D or self.scales.dtype != x.dtype:
+            raise RuntimeError("appended tensor does not match the cache: "
+                               f"expected [B={self.codes.size(0)},H={self.codes.size(1)},n,D={self.D}] {self.scales.dtype}")
+        cap = self.codes.size(2)
+        if need > cap:
+            new_cap = 1 << (need - 1).bit_length()
+            codes = torch.empty((B, H, new_cap, W), dtype=self.codes.dtype, device=x.device)
+            codes[:, :, : self.T].copy_(self.codes[:, :, : self.T])
+            scales = torch.empty(new_cap, dtype=self.scales.dtype, device=x.device)
+            scales[: self.T].copy_(self.scales[: self.T])
+            s32 = torch.empty(new_cap, dtype=torch.float32, device=x.device)
+            s32[: self.T].copy_(self.scales_f32[: self.T])
+            self.codes, self.scales, self.scales_f32 = codes, scales, s32
+
+    def append_per_token(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
+        """n tokens, one scale each, in one launch (two + an allreduce when head-sharded)."""
+        n = x.size(2)
+        self._reserve(x, n)
+        dst = self.codes[:, :, self.T: self.T + n]
+        sc = self.scales[self.T: self.T + n]
+        s32 = self.scales_f32[self.T: self.T + n]
+        sh, st = L.shape_stride(x)
+        lib, dt, stream = L.lib(), L.dtype_code(x.dtype), L.stream_ptr(x.device)
+        if group is None:
+            bits = torch.empty(n, dtype=torch.int32, device=x.device)
+            L.check(lib.kvq_quant_per_token_fused(x.data_ptr(), dt, sh, st, self.bits, float(eps), dst.data_ptr(),
+                                                  L.stride3(dst), sc.data_ptr(), s32.data_ptr(), bits.data_ptr(), stream),
+                    "kvq_quant_per_token_fused")
+            L.count_launch()
+        else:
+            bits = _absmax_bits(x, L.PER_TOKEN, group)
+            fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
+            L.check(fn(x.data_ptr(), dt, sh, st, L.PER_TOKEN, bits.data_ptr(), float(eps), dst.data_ptr(), L.stride3(dst),
+                       sc.data_ptr(), s32.data_ptr(), stream), "kvq_quant (per token)")
+            L.count_launch()
+        self.T += n
+        self.n_scale_entries += n
+
+    def append_shared_scale(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
+        """The reference's append() given n > 1 tokens: ONE scale over the whole [B,H,n,D] block
+        (ops.py:181-210 calls the per-tensor helper on whatever it is handed)."""
+        n = x.size(2)
+        self._reserve(x, n)
+        dst = self.codes[:, :, self.T: self.T + n]
+        bits = _absmax_bits(x, L.PER_TENSOR, group)
+        one = torch.empty(1, dtype=x.dtype, device=x.device)
+        one32 = torch.empty(1, dtype=torch.float32, device=x.device)
+        sh, st = L.shape_stride(x)
+        fn = L.lib().kvq_quant_int8 if self.bits == 8 else L.lib().kvq_quant_int4_pack
+        L.check(fn(x.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(), float(eps), dst.data_ptr(),
+                   L.stride3(dst), one.data_ptr(), one32.data_ptr(), L.stream_ptr(x.device)), "kvq_quant (block)")
+        L.count_launch()
+        self.scales[self.T: self.T + n] = one
+        self.scales_f32[self.T: self.T + n] = one32
+        self.T += n
+        self.n_scale_entries += 1
+
+    def dequantize(self, out_dtype: torch.dtype) -> torch.Tensor:
+        B, H = self.codes.shape[:2]
+        out = torch.empty((B, H, self.T, self.D), dtype=out_dtype, device=self.codes.device)
+        src = self.codes[:, :, : self.T]
+        sh = L.I64x4(B, H, self.T, self.D)
+        fn = L.lib().kvq_dequant_int8 if self.bits == 8 else L.lib().kvq_dequant_int4_unpack
+        L.check(fn(src.data_ptr(), sh, L.stride3(src), self.scales.data_ptr(), L.dtype_code(self.scales.dtype), L.PER_TOKEN,
+                   out.data_ptr(), L.dtype_code(out_dtype), L.stream_ptr(out.device)), "kvq_dequant (per token)")
+        L.count_launch()
+        return out
+
+    def nbytes(self) -> int:
+        if self.codes is None:
+            return 0
+        B, H, _, W = self.codes.shape
+        return B * H * self.T * W * self.codes.element_size() + self.n_scale_entries * self.scales.element_size()
+
+    def token_views(self) -> List[torch.Tensor]:
+        return [] if self.codes is None else [self.codes[:, :, t: t + 1] for t in range(self.T)]
+
+    def scale_views(self) -> List[torch.Tensor]:
+        return [] if self.scales is None else [self.scales[t] for t in range(self.T)]
+
+
+class QuantizedLayerKV:
+    """Quantized KV cache of one transformer layer.
+
+    mode "int8": K and V INT8; "int4": both packed INT4; "mixed": K INT8, V INT4.
+    (reference ops.py:136-290)
+    """
+
+    def __init__(self, mode: str = "int8", device: str = "cuda", compute_dtype: torch.dtype = torch.float16,
+                 group=None):
+        assert mode in ["int8", "int4", "mixed"], f"Invalid mode: {mode}"
+        self.mode = mode
+        self.device = device
+        self.compute_dtype = compute_dtype
+        self.group = group  # torch.distributed group of a head-sharded cache (None: single GPU)
+        self._k = _TokenStore(4 if mode == "int4" else 8)
+        self._v = _TokenStore(8 if mode == "int8" else 4)
+
+    # --- reference-visible storage, as views of the contiguous store ----------------------------
+    @property
+    def k_store(self) -> List[torch.Tensor]:
+        return self._k.token_views()
+
+    @property
+    def v_store(self) -> List[torch.Tensor]:
+        return self._v.token_views()
+
+    @property
+    def k_scales(self) -> List[torch.Tensor]:
+        return self._k.scale_views()
+
+    @property
+    def v_scales(self) -> List[torch.Tensor]:
+        return self._v.scale_views()
+
+    @property
+    def k_meta(self) -> List[Optional[int]]:
+        return [self._k.D if self._k.bits == 4 else None] * self._k.T
+
+    @property
+    def v_meta(self) -> List[Optional[int]]:
+        return [self._v.D if self._v.bits == 4 else None] * self._v.T
+
+    def __len__(self) -> int:
+        return self._k.T
+
+    @staticmethod
+    def _check_pair(k: torch.Tensor, v: torch.Tensor) -> None:
+        L.require_cuda(k, v)
+        if k.dim() != 4 or v.dim() != 4:
+            raise RuntimeError("expected K and V of shape [B, H, n, D]")
+        if k.numel() == 0 or v.numel() == 0:
+            raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0")
+
+    @torch.no_grad()
+    def append(self, k_1tok: torch.Tensor, v_1tok: torch.Tensor) -> None:
+        """Append one token's K and V, each [B,H,1,D], quantized with its own scale."""
+        self._check_pair(k_1tok, v_1tok)
+        with L.device_guard(k_1tok):
+            for store, x in ((self._k, k_1tok), (self._v, v_1tok)):
+                if x.size(2) == 1:
+                    store.append_per_token(x, group=self.group)
+                else:
+                    store.append_shared_scale(x, group=self.group)
+
+    @torch.no_grad()
+    def append_tokens(self, k: torch.Tensor, v: torch.Tensor) -> None:
+        """Append n tokens [B,H,n,D], each with its own scale: identical to n append() calls of one
+        token each (what init_from_prompt_past does, ops.py:339-342), in one launch per tensor."""
+        self._check_pair(k, v)
+        with L.device_guard(k):
+            self._k.append_per_token(k, group=self.group)
+            self._v.append_per_token(v, group=self.group)
+
+    @torch.no_grad()
+    def get_kv(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Dequantized (K, V), each [B,H,T,D] in compute_dtype."""
+        if self._k.T == 0:
+            raise ValueError("Empty cache")
+        with L.device_guard(self._k.codes):
+            return self._k.dequantize(self.compute_dtype), self._v.dequantize(self.compute_dtype)
+
+    def quantized(self):
+        """(k_codes, k_scales_f32, k_bits, v_codes, v_scales_f32, v_bits) views of the live store, for
+        the fused dequant decode attention."""
+        if self._k.T == 0:
+            raise ValueError("Empty cache")
+        T = self._k.T
+        return (self._k.codes[:, :, :T], self._k.scales_f32[:T], self._k.bits,
+                self._v.codes[:, :, :T], self._v.scales_f32[:T], self._v.bits)
+
+    def estimated_bytes(self) -> int:
+        """Stored codes + scales, as the reference counts them (ops.py:271-290)."""
+        return self._k.nbytes() + self._v.nbytes()
+
+
+class QuantizedKVCache:
+    """Quantized caches of all layers (reference ops.py:293-363)."""
+
+    def __init__(self, n_layers: int, mode: str = "int8", device: str = "cuda",
+                 compute_dtype: torch.dtype = torch.float16, group=None):
+        self.layers = [QuantizedLayerKV(mode=mode, device=device, compute_dtype=compute_dtype, group=group)
+                       for _ in range(n_layers)]
+
+    @torch.no_grad()
+    def append_from_past(self, past_key_values: tuple) -> None:
+        """Append the last token of every layer's (k, v)."""
+        for i, (k, v) in enumerate(past_key_values):
+            self.layers[i].append(k[:, :, -1:, :], v[:, :, -1:, :])
+
+    @torch.no_grad()
+    def init_from_prompt_past(self, past_key_values: tuple) -> None:
+        """Quantize the whole prompt, one scale per token (the reference loops over t, ops.py:339-342)."""
+        for layer_idx, (k, v) in enumerate(past_key_values):
+            if k.size(2) > 0:
+                self.layers[layer_idx].append_tokens(k, v)
+
+    @torch.no_grad()
+    def to_past_key_values(self) -> tuple:
+        return tuple(layer.get_kv() for layer in self.layers)
+
+    def estimated_bytes(self) -> int:
+        return sum(layer.estimated_bytes() for layer in self.layers)

@@ -1,0 +1,229 @@
+/*
+ * kvq.h -- C ABI of libkvq_sm100.so: the B200-native (sm_100a) KV-cache hot path of
+ * Efficient-LLM-Inference.
+ *
+ * This is the drop-in boundary.  The reference's only native interface is the pybind11 module
+ * `kvq_ext` JIT-built from an inline string (src/cuda/extensions.py:116-130, reached through
+ * get_cuda_extension() :138-147 and called at src/quantization/ops.py:87 and :116-118).  Every entry
+ * point below names the reference interface it replaces.  Paths are relative to /root/reference.
+ *
+ * Conventions
+ *  - plain pointers and sizes only: no torch / pybind types.  All data pointers are DEVICE pointers
+ *    unless the parameter name ends in `_host`.
+ *  - the caller owns all memory; the library never allocates or frees device memory and keeps no
+ *    global device state.  Every launch goes to the caller's `stream` (the reference launches on the
+ *    legacy default stream, extensions.py:79,105 -- a bug this ABI does not inherit).
+ *  - every function returns KVQ_OK (0) or a negative kvq_status; kvq_last_error() returns the
+ *    thread-local message of the last failure (the reference raises RuntimeError through TORCH_CHECK,
+ *    extensions.py:33-35,72,90,93; the Python wrapper turns non-zero into RuntimeError).
+ *  - tensors are 4-D [B, H, T, D] ("batch, kv head, token, head_dim", ops.py:178-179) given as
+ *    shape[4] and stride[4] in ELEMENTS; inputs may be views (k[:, :, t:t+1, :], transposed HF
+ *    layouts).  Code / output tensors are given with stride3 = {sB, sH, sT} in elements of that
+ *    tensor and a contiguous last dimension; stride3 == NULL means contiguous.
+ *  - dtype codes: KVQ_F32 / KVQ_F16 / KVQ_BF16.
+ *  - scales never leave the device (the reference syncs with float(scale) per call, ops.py:87,117).
+ */
+#ifndef KVQ_H_
+#define KVQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVQ_VERSION 100
+
+#if defined(__GNUC__)
+#define KVQ_API __attribute__((visibility("default")))
+#else
+#define KVQ_API
+#endif
+
+typedef void* kvq_stream_t; /* cudaStream_t */
+
+enum kvq_dtype { KVQ_F32 = 0, KVQ_F16 = 1, KVQ_BF16 = 2 };
+
+enum kvq_status {
+    KVQ_OK = 0,
+    KVQ_ERR_INVALID = -1,     /* bad argument (shape, dtype, alignment the path cannot take) */
+    KVQ_ERR_CUDA = -2,        /* a CUDA runtime call / launch failed; message has the CUDA error */
+    KVQ_ERR_UNSUPPORTED = -3, /* valid request this build does not implement */
+    KVQ_ERR_NO_DEVICE = -4    /* no sm_100 device visible */
+};
+
+/* granularity of the quantization scale */
+enum kvq_granularity {
+    KVQ_PER_TENSOR = 0, /* one scale for the whole tensor: the helpers called directly, ops.py:10-65 */
+    KVQ_PER_TOKEN = 1   /* one scale per token t shared by all (b, h, d): what QuantizedKVCache produces by
+                           calling the helpers on x[:, :, t:t+1, :] (ops.py:323-342) */
+};
+
+/* eviction strategies of src/cache/implementations.py */
+enum kvq_evict_strategy {
+    KVQ_EVICT_SLIDING = 0,       /* trim_kv_sliding_window  :124-140 */
+    KVQ_EVICT_PREFIX_WINDOW = 1, /* trim_kv_prefix_window   :143-154 */
+    KVQ_EVICT_STRIDED = 2,       /* trim_kv_strided         :157-190 */
+    KVQ_EVICT_BLOCK = 3,         /* trim_kv_block_old       :193-245 */
+    KVQ_EVICT_BUDGET = 4         /* trim_kv_budget_old      :248-292 */
+};
+
+/* ---------------------------------------------------------------------------------- library */
+
+KVQ_API int kvq_version(void);
+KVQ_API const char* kvq_last_error(void);
+/* SM count / compute capability of the current device; KVQ_ERR_NO_DEVICE when it is not sm_100. */
+KVQ_API int kvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------- area 1: quantize
+ * Two-phase pair (north_star area 1).  Phase 1 reduces max|x| as the BIT PATTERN of a non-negative
+ * fp32 (uint32 order == float order), so that partial results combine with integer max: across
+ * CTAs by atomicMax, across head-sharded GPUs by an allreduce(MAX).  Phase 2 turns the max into the
+ * scale and writes codes.
+ *
+ *   scale  = max(absmax / qmax, eps)           fp32 division     ops.py:28 (qmax 127), :49 (qmax 7)
+ *   code   = clamp(rint(x / scale), lo, hi)    half-to-even      ops.py:29, :50
+ *   returned scale = scale rounded to x's dtype                  ops.py:30, :65
+ */
+
+/* Phase 1.  absmax_bits: 1 word (per tensor) or T words (per token).  The words are max-combined
+ * with their current contents when accumulate != 0 (zero them first for a fresh reduction, or chain
+ * several shards into one word); otherwise they are overwritten.
+ * Replaces: x_fp32.abs().max()  ops.py:26-27, :47-48. */
+KVQ_API int kvq_absmax(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int granularity,
+               uint32_t* absmax_bits, int accumulate, kvq_stream_t stream);
+
+/* Phase 2, INT8.  q: int8 codes [B,H,T,D] with q_stride3.  scale_out (nullable): 1 or T elements of
+ * x's dtype = scale.to(x.dtype).  scale_f32_out (nullable): the same rounded value widened to fp32
+ * (what dequantize multiplies by, ops.py:90).
+ * Replaces: quantize_int8_per_tensor  ops.py:10-30. */
+KVQ_API int kvq_quant_int8(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int granularity,
+                   const uint32_t* absmax_bits, float eps, int8_t* q, const int64_t q_stride3[3],
+                   void* scale_out, float* scale_f32_out, kvq_stream_t stream);
+
+/* Phase 2, INT4 nibble-packed: byte j of a row holds element 2j in the HIGH nibble and 2j+1 in the low
+ * nibble, each as code+8; an odd D is padded with one zero code (nibble 8).  packed: uint8
+ * [B,H,T,ceil(D/2)].  Replaces: quantize_int4_per_tensor_packed  ops.py:33-65. */
+KVQ_API int kvq_quant_int4_pack(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
+                        int granularity, const uint32_t* absmax_bits, float eps, uint8_t* packed,
+                        const int64_t q_stride3[3], void* scale_out, float* scale_f32_out,
+                        kvq_stream_t stream);
+
+/* Single-pass per-token quantize: one CTA owns whole tokens, reduces max|x| over (b,h,d) on chip and
+ * writes codes without re-reading HBM.  bits = 8 or 4.  Also writes absmax_bits_out[T] when non-NULL.
+ * Replaces the per-token loop  QuantizedKVCache.init_from_prompt_past / append_from_past
+ * (ops.py:323-342) -> QuantizedLayerKV.append (ops.py:174-210). */
+KVQ_API int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int bits,
+                              float eps, void* q, const int64_t q_stride3[3], void* scale_out,
+                              float* scale_f32_out, uint32_t* absmax_bits_out, kvq_stream_t stream);
+
+/* ---------------------------------------------------------------------------------- area 1: dequantize
+ *   out = (float(code) * float(scale)) rounded to out_dtype      ops.py:90, :122-133
+ * scale: 1 (per tensor) or T (per token) elements of scale_dtype, on the device. */
+
+/* Replaces: dequantize_int8_per_tensor ops.py:68-90 and kvq_ext.dequant_int8_to_fp16
+ * (extensions.py:37-48,70-86). */
+KVQ_API int kvq_dequant_int8(const int8_t* q, const int64_t shape[4], const int64_t q_stride3[3], const void* scale,
+                     int scale_dtype, int granularity, void* out, int out_dtype, kvq_stream_t stream);
+
+/* shape[3] = orig_last_dim (elements per output row); packed rows hold ceil(orig_last/2) bytes.
+ * Replaces: dequantize_int4_per_tensor_packed ops.py:93-133 and kvq_ext.dequant_int4_packed_to_fp16
+ * (extensions.py:50-68,88-114). */
+KVQ_API int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shape[4], const int64_t q_stride3[3],
+                            const void* scale, int scale_dtype, int granularity, void* out, int out_dtype,
+                            kvq_stream_t stream);
+
+/* ---------------------------------------------------------------------------------- area 2: eviction
+ * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
+ * of every destination row in registers; no index tensor and no intermediate parts list exists. */
+
+typedef struct kvq_evict_plan {
+    int32_t strategy;
+    int32_t identity;     /* 1: cache unchanged (T <= prefix + window, or sliding with T <= window) */
+    int64_t T;            /* source length */
+    int64_t n_prefix;     /* rows copied from [0, n_prefix) */
+    int64_t n_old;        /* rows taken from the older region [old_start, tail_start) */
+    int64_t old_start;    /* = prefix_len */
+    int64_t tail_start;   /* rows [tail_start, tail_start + n_tail) copied at the end */
+    int64_t n_tail;
+    int64_t n_total;      /* = n_prefix + n_old + n_tail : the new cache length */
+    int64_t stride;       /* strided: step; block: block_size */
+    int64_t keep;         /* block: keep_per_block */
+    int64_t budget;       /* budget: linspace steps (0 when the whole older region is kept) */
+    int32_t needs_table;  /* budget only: float32 linspace produced duplicates that
+                             unique_consecutive removed -> the older region needs kvq_evict_indices_host
+                             + table mode (never seen for budget < old_len / 2) */
+    int32_t reserved;
+} kvq_evict_plan;
+
+/* Host, pure arithmetic (no CUDA): fills *plan for a cache of length T.  Returns KVQ_ERR_INVALID for
+ * stride < 1, block < 1, keep outside [1, block], budget < 0, negative window / prefix (the
+ * reference asserts the first four: implementations.py:164,207-208,257). */
+KVQ_API int kvq_evict_plan_make(int strategy, int64_t T, int64_t window, int64_t prefix, int64_t stride, int64_t block,
+                        int64_t keep, int64_t budget, kvq_evict_plan* plan);
+
+/* Host: writes plan->n_total kept source indices (the reference's idx / cat order). */
+KVQ_API int kvq_evict_indices_host(const kvq_evict_plan* plan, int64_t* idx_host);
+
+/* Device: the same indices computed by the device function the gather kernel uses (parity probe). */
+KVQ_API int kvq_evict_indices_device(const kvq_evict_plan* plan, const int32_t* old_table, int64_t* idx,
+                             kvq_stream_t stream);
+
+/* dst[b,h,j,:] = src[b,h,index(j),:] for j < plan->n_total.  elem_bytes = bytes per element of the rows
+ * (2 for fp16/bf16, 4 fp32, 1 for INT8 codes / packed INT4 bytes: the same kernel compacts a quantized
+ * store).  old_table (nullable, int32[n_old]): source tokens of the older region when
+ * plan->needs_table.  Replaces: trim_kv_* implementations.py:124-292 (slicing, arange,
+ * index_select, linspace, unique_consecutive, cat). */
+KVQ_API int kvq_evict_gather(const void* src, int elem_bytes, const int64_t shape[4], const int64_t stride[4],
+                     const kvq_evict_plan* plan, const int32_t* old_table, void* dst,
+                     const int64_t dst_stride3[3], kvq_stream_t stream);
+
+/* ---------------------------------------------------------------------------------- area 2: paged store
+ * Physical pool [n_blocks, B, H, block_size, D]; block_table[i] = physical block of logical block i.
+ * The reference keeps a Python list of [B,H,block,D] tensors whose list index is the logical block
+ * (implementations.py:36-54). */
+
+/* Writes one token (x is [B,H,1,D], strided) into slot t % block_size of logical block t / block_size.
+ * Replaces: PagedKVCache.append implementations.py:57-80. */
+KVQ_API int kvq_paged_append(const void* x, int elem_bytes, const int64_t shape[4], const int64_t stride[4], void* pool,
+                     const int32_t* block_table, int64_t block_size, int64_t t, kvq_stream_t stream);
+
+/* Stitches the first T tokens into contiguous out [B,H,T,D].  shape = {B,H,T,D}.
+ * Replaces: PagedKVCache.get_kv implementations.py:83-106. */
+KVQ_API int kvq_paged_gather(const void* pool, int elem_bytes, const int64_t shape[4], const int32_t* block_table,
+                     int64_t block_size, void* out, kvq_stream_t stream);
+
+/* ---------------------------------------------------------------------------------- area 3: chunk summary
+ * out[b,h,c,:]            = sum_{t in chunk c of [0,old_len)} x[b,h,t,:] / chunk_size   (c < n_chunks)
+ * out[b,h,n_chunks + r,:] = x[b,h,old_len + r,:]                                        (r < keep_eff)
+ * with keep_eff = min(keep_last, T), old_len = T - keep_eff, n_chunks = ceil(old_len / chunk).  The last,
+ * zero-padded chunk is divided by chunk_size like the others (implementations.py:326-339).  fp32
+ * accumulation, one rounding to the dtype.  out is contiguous [B,H,n_chunks+keep_eff,D].
+ * Replaces: chunk_summarize_kv implementations.py:295-346 (pad-cat, view, mean, cat). */
+KVQ_API int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int64_t chunk,
+                   int64_t keep_last, void* out, kvq_stream_t stream);
+
+/* ---------------------------------------------------------------------------------- area 4: decode attention
+ * One decode step over a per-token-quantized cache, dequantizing K/V in registers (split-K GEMV, no
+ * tensor cores):   out[b,hq,:] = softmax_t( q[b,hq,:] . K[b,hq/G,t,:] * sm_scale ) V[b,hq/G,t,:]
+ * with K[.,t,:] = k_codes * k_scale[t], V likewise.  The reference hands the dequantized cache to
+ * transformers' attention (benchmarker.py:470-477); this entry replaces dequantize-everything +
+ * DynamicCache + attention for the cached tokens.
+ *   q        [B, Hq, D]   q_dtype, contiguous
+ *   k_codes  k_bits 8: int8 [B,H,T,D];  4: uint8 [B,H,T,D/2]  (k_stride3 in bytes of that tensor)
+ *   k_scale  fp32 [T]  (the rounded scales, see kvq_quant_* scale_f32_out)
+ *   v_codes / v_scale likewise
+ *   out      [B, Hq, D]   out_dtype, contiguous
+ *   workspace: kvq_decode_attn_workspace_bytes(...) bytes, n_splits as returned there
+ * D must be 64 or 128. */
+KVQ_API int64_t kvq_decode_attn_workspace_bytes(int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, int* n_splits);
+
+KVQ_API int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                    const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                    const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                    void* out, int out_dtype, void* workspace, int n_splits, kvq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVQ_H_ */

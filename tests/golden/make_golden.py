@@ -10,6 +10,7 @@ Fixture files
   quant.npz      per-tensor INT8 / INT4 quantize + dequantize (ops.py:10-133), KATs of SURVEY section 4
   pertoken.npz   QuantizedLayerKV append/get_kv/estimated_bytes in int8 / int4 / mixed (ops.py:136-290)
   evict.npz      index sets of trim_kv_* (implementations.py:124-292) over a parameter sweep
+  evict_big.npz  million-token budget cases with float32-linspace duplicates (delta encoded)
   chunk.npz      chunk_summarize_kv (implementations.py:295-346)
   paged.npz      PagedKVCache append/get_kv/bytes (implementations.py:10-121)
   attn.npz       fp32 eager attention over the reference's dequantized cache (benchmarker.py:470-477)
@@ -168,6 +169,21 @@ def make_evict():
     np.savez_compressed(os.path.join(HERE, "evict.npz"), **out)
 
 
+def make_evict_big():
+    """Million-token budget cases where float32 linspace yields duplicates that unique_consecutive removes
+    (the kernel's table mode).  Stored as first index + int8 deltas (the lists are ~1M long)."""
+    out = {}
+    rows = [(964858, 148, 1, 951071), (1367489, 194, 13, 1364206), (1000003, 256, 0, 999000)]
+    for i, (T, w, p, bud) in enumerate(rows):
+        idx = index_set(rc.trim_kv_budget_old, T, window_size=w, old_budget=bud, prefix_len=p)
+        d = np.diff(idx)
+        assert d.min() >= 0 and d.max() < 127
+        out[f"{i}/first"] = np.int64(idx[0])
+        out[f"{i}/deltas"] = d.astype(np.int8)
+    out["params"] = np.array(rows, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "evict_big.npz"), **out)
+
+
 def make_chunk():
     out = {}
     cases = []
@@ -242,6 +258,7 @@ if __name__ == "__main__":
     make_quant()
     make_pertoken()
     make_evict()
+    make_evict_big()
     make_chunk()
     make_paged()
     make_attn()

