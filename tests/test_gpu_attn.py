@@ -1,7 +1,8 @@
 """Area 4 on the GPU: fused dequant decode attention against the golden fp32 eager attention over the
 reference's dequantized cache and against the oracle.  Tolerance (stated): fp32 accumulation with a
-different summation order and exp2-domain softmax -> rtol 1e-4 / atol 1e-5 for fp32 outputs;
-2e-3 for fp16 / bf16 outputs (one rounding of q and of the result)."""
+different summation order and exp2-domain softmax -> rtol 1e-4 / atol 1e-5 for fp32 outputs; for 16-bit
+outputs one more rounding of the result: fp16 rtol = atol = 2e-3 (2^-11 relative + slack), bf16
+rtol = atol = 8e-3 (2^-8 relative)."""
 
 import pytest
 import torch
@@ -54,7 +55,8 @@ def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
         o16 = kvq.decode_attention_quantized(q.cuda().to(dt), kc, ks, kb, vc, vs, vb)
         want16 = oracle.decode_attention(q.to(dt).float(), kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
         assert o16.dtype == dt
-        torch.testing.assert_close(o16.cpu().float(), want16, rtol=2e-3, atol=2e-3)
+        tol = 2e-3 if dt == torch.float16 else 8e-3
+        torch.testing.assert_close(o16.cpu().float(), want16, rtol=tol, atol=tol)
 
 
 def test_matches_dequantize_then_attend(kvq):

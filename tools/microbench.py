@@ -23,6 +23,8 @@ except Exception:
 
 
 def timeit(fn, iters=20, warm=3):
+    iters = int(os.environ.get('MB_ITERS', iters))
+    warm = int(os.environ.get('MB_WARM', warm))
     for _ in range(warm):
         fn(0)
     torch.cuda.synchronize()
