@@ -6,12 +6,16 @@
 //   INT4: byte j = ((code[2j]+8) << 4) | (code[2j+1]+8), odd D padded with nibble 8   :53-63
 //   dequant = (float(code) * float(scale.to(x.dtype))) -> out dtype          :90, :122-133
 //
-// Everything here is HBM-bound streaming work: 128-bit coalesced loads/stores, several loads in
-// flight per thread, warp REDUX + one atomicMax per CTA for the max.  The per-element division is
-// replaced, for 16-bit inputs, by y = RN(1/scale); q0 = RN(x*y); r = fma(-q0,scale,x);
-// q1 = fma(r,y,q0), which gives the same code as rint(x/scale) for EVERY fp16/bf16 x and every
-// possible scale (proved by exhaustion: oracle kvqo_check_division_free, tests/test_exact_division.py).
-// fp32 inputs use the IEEE division (__fdiv_rn).
+// Everything here is HBM-bound streaming work.  The unit of work is one 16-byte vector per lane, so
+// every warp-level load and store covers one contiguous, fully used run of sectors; a thread keeps
+// several vectors in flight, and all kernels are grid-stride loops so that per-thread setup is
+// amortised (the first version spent half its issue slots on address arithmetic).  The max is reduced
+// with REDUX per warp and one atomicMax per CTA.
+//
+// The per-element division is replaced, for 16-bit inputs, by y = RN(1/scale); q0 = RN(x*y);
+// r = fma(-q0,scale,x); q1 = fma(r,y,q0), which gives the same code as rint(x/scale) for EVERY
+// fp16/bf16 x and every possible scale (proved by exhaustion: oracle kvqo_check_division_free,
+// tests/test_exact_division.py).  fp32 inputs use the IEEE division (__fdiv_rn).
 #include "kvq_common.cuh"
 
 namespace kvq {
@@ -56,234 +60,291 @@ __device__ __forceinline__ uint32_t pack4_bytes(uint32_t a, uint32_t b, uint32_t
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
-// ---- a 16-element item: raw registers, widening, absmax, quantize+pack ---------------------------------
+// ---- one 16-byte input vector: 8 fp16/bf16 or 4 fp32 elements ------------------------------------------
 
-template <int DT> struct Item16 {
-    static constexpr int kVecs = DT == KVQ_F32 ? 4 : 2;  // 16-byte vectors per 16 elements
-    uint4 v[kVecs];
+template <int DT> struct InVec {
+    static constexpr int kN = 16 / ElemT<DT>::kSize;
 
-    __device__ __forceinline__ void load(const void* p) {
-#pragma unroll
-        for (int i = 0; i < kVecs; ++i) v[i] = ld_stream(reinterpret_cast<const uint4*>(p) + i);
-    }
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < kVecs; ++i) v[i] = make_uint4(0, 0, 0, 0);
-    }
     // max |x| as fp32 bits
-    __device__ __forceinline__ uint32_t absmax_bits() const {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
+    static __device__ __forceinline__ uint32_t absmax_bits(const uint4& v) {
         if (DT == KVQ_F32) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m = max(m, w[i] & 0x7fffffffu);
-            return m;
+            return max(max(v.x & 0x7fffffffu, v.y & 0x7fffffffu), max(v.z & 0x7fffffffu, v.w & 0x7fffffffu));
         }
         // packed 16-bit: clear both sign bits, unsigned 16-bit SIMD max (bit order == value order)
-        uint32_t m = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m = __vmaxu2(m, w[i] & 0x7fff7fffu);
+        const uint32_t m = __vmaxu2(__vmaxu2(v.x & 0x7fff7fffu, v.y & 0x7fff7fffu), __vmaxu2(v.z & 0x7fff7fffu, v.w & 0x7fff7fffu));
+        return m;  // still packed: finish with finish_absmax()
+    }
+    // packed running max -> fp32 bits (call once per thread, not per vector)
+    static __device__ __forceinline__ uint32_t finish_absmax(uint32_t m) {
+        if (DT == KVQ_F32) return m;
         const uint32_t h = max(m & 0xffffu, m >> 16);
         if (DT == KVQ_BF16) return h << 16;
         return __float_as_uint(__half2float(__ushort_as_half((unsigned short)h)));
     }
-    __device__ __forceinline__ void widen(float f[16]) const {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
+    static __device__ __forceinline__ uint32_t combine(uint32_t a, uint32_t b) {
+        return DT == KVQ_F32 ? max(a, b) : __vmaxu2(a, b);
+    }
+    static __device__ __forceinline__ void widen(const uint4& v, float f[kN]) {
         if (DT == KVQ_F32) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(w[i]);
+            f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
         } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) widen2<DT>(w[i], f[2 * i], f[2 * i + 1]);
+            widen2<DT>(v.x, f[0], f[1]); widen2<DT>(v.y, f[2], f[3]); widen2<DT>(v.z, f[4], f[5]); widen2<DT>(v.w, f[6], f[7]);
         }
     }
-    // 16 int8 codes
-    __device__ __forceinline__ uint4 quant8(const Scale& sc) const {
-        float f[16];
-        widen(f);
-        uint32_t c[16];
+};
+
+// codes of one input vector, stored at `out` (naturally aligned): kN bytes (INT8) or kN/2 bytes (INT4)
+template <int DT, int BITS> __device__ __forceinline__ void quant_store(const uint4& v, const Scale& sc, void* out) {
+    constexpr int kN = InVec<DT>::kN;
+    float f[kN];
+    InVec<DT>::widen(v, f);
+    if constexpr (BITS == 8) {
+        uint32_t c[kN];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = code_word<DT, 8>(f[i], sc);
-        return make_uint4(pack4_bytes(c[0], c[1], c[2], c[3]), pack4_bytes(c[4], c[5], c[6], c[7]),
-                          pack4_bytes(c[8], c[9], c[10], c[11]), pack4_bytes(c[12], c[13], c[14], c[15]));
-    }
-    // 8 bytes of packed nibbles (even element -> high nibble)
-    __device__ __forceinline__ uint2 quant4(const Scale& sc) const {
-        float f[16];
-        widen(f);
-        uint32_t b[8];
+        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8>(f[i], sc);
+        if constexpr (kN == 8) st_stream8(out, make_uint2(pack4_bytes(c[0], c[1], c[2], c[3]), pack4_bytes(c[4], c[5], c[6], c[7])));
+        else st_stream4(out, pack4_bytes(c[0], c[1], c[2], c[3]));
+    } else {
+        uint32_t b[kN / 2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < kN / 2; ++i)
             b[i] = code_word<DT, 4>(f[2 * i], sc) * 16u + code_word<DT, 4>(f[2 * i + 1], sc);  // low byte valid
-        return make_uint2(pack4_bytes(b[0], b[1], b[2], b[3]), pack4_bytes(b[4], b[5], b[6], b[7]));
+        if constexpr (kN == 8) st_stream4(out, pack4_bytes(b[0], b[1], b[2], b[3]));
+        else *reinterpret_cast<unsigned short*>(out) = (unsigned short)(__byte_perm(b[0], b[1], 0x0040) & 0xffffu);
     }
-};
-
-// ---- row-tiled addressing shared by the streaming kernels -------------------------------------------
-// A "plane" is one (b, h); a CTA covers UNROLL * rows_per_pass tokens of one plane; a thread owns the
-// 16-element item `c` of a row, so no per-item division is needed.
-
-struct RowGeom {
-    int64_t nP, H;          // planes = B*H (H only used to split p when planes are not uniform)
-    int64_t T;              // rows per plane
-    int64_t xB, xH, xT;     // input strides (elements)
-    int64_t qB, qH, qT;     // output strides (elements of the output tensor)
-    int ipr;                // 16-element items per row (D / 16)
-};
-
-__device__ __forceinline__ void plane_offsets(const RowGeom& g, int64_t p, int64_t& xo, int64_t& qo) {
-    const int b = (int)p / (int)g.H, h = (int)p - b * (int)g.H;
-    xo = b * g.xB + h * g.xH;
-    qo = b * g.qB + h * g.qH;
 }
+template <int DT, int BITS> struct OutBytes { static constexpr int value = InVec<DT>::kN * BITS / 8; };
 
-// ---- phase 1: per-tensor absmax ---------------------------------------------------------------------
+// ---- flat kernels: contiguous input and output, per-tensor scale ---------------------------------------------
 
 template <int DT, int UNROLL>
-__global__ void __launch_bounds__(kThreads) absmax_rows_kernel(const void* __restrict__ x, RowGeom g,
+__global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
                                                                uint32_t* __restrict__ absmax_bits) {
     __shared__ uint32_t red[kThreads / 32];
-    const int c = threadIdx.x % g.ipr, r0 = threadIdx.x / g.ipr, rpp = kThreads / g.ipr;
     uint32_t m = 0;
-    if (r0 < rpp) {
-        for (int64_t p = blockIdx.y; p < g.nP; p += gridDim.y) {
-            int64_t xo, qo;
-            plane_offsets(g, p, xo, qo);
-            const char* base = reinterpret_cast<const char*>(x) + (xo + (int64_t)c * 16) * ElemT<DT>::kSize;
-            const int64_t t0 = (int64_t)blockIdx.x * rpp * UNROLL + r0;
-            Item16<DT> it[UNROLL];
+    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        uint4 v[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t t = t0 + (int64_t)u * rpp;
-                if (t < g.T) it[u].load(base + t * g.xT * ElemT<DT>::kSize); else it[u].zero();
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) m = max(m, it[u].absmax_bits());
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            v[u] = j < n_vec ? ld_stream(x + j) : make_uint4(0, 0, 0, 0);
         }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
     }
-    m = block_max_u32<kThreads>(m, red);
+    m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
     if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits, m);
 }
 
-// ---- phase 2: quantize rows given absmax (per tensor or per token) ---------------------------------------
+template <int DT, int BITS, int UNROLL>
+__global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
+                                                              const uint32_t* __restrict__ absmax_bits, float eps,
+                                                              char* __restrict__ q, void* __restrict__ scale_out,
+                                                              float* __restrict__ scale_f32_out) {
+    constexpr int kOut = OutBytes<DT, BITS>::value;
+    const Scale sc = scale_from_bits<BITS>(absmax_bits[0], eps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (scale_out) store_scalar<DT>(scale_out, 0, sc.s);
+        if (scale_f32_out) scale_f32_out[0] = round_through<DT>(sc.s);
+    }
+    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) v[u] = ld_stream(x + j);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) quant_store<DT, BITS>(v[u], sc, q + j * kOut);
+        }
+    }
+}
+
+// ---- strided rows: a "plane" is one (b, h); a CTA walks tiles of UNROLL * rows-per-pass tokens --------------
+
+struct RowGeom {
+    int nP, H;              // planes, and the divisor that splits a plane index into (b, h); H == 1: p -> b
+    int64_t T;              // rows (tokens) per plane
+    int64_t xB, xH, xT;     // input strides in BYTES
+    int64_t qB, qH, qT;     // output strides in BYTES
+    int vpr;                // 16-byte vectors per row on the 16-byte side
+    int shift;              // log2(vpr) when vpr is a power of two, else -1
+};
+
+__device__ __forceinline__ void plane_offsets(const RowGeom& g, int p, int64_t& xo, int64_t& qo) {
+    const int b = g.H == 1 ? p : p / g.H, h = p - b * g.H;
+    xo = b * g.xB + h * g.xH;
+    qo = b * g.qB + h * g.qH;
+}
+__device__ __forceinline__ void split_thread(const RowGeom& g, int tid, int& c, int& r0, int& rpp) {
+    if (g.shift >= 0) { c = tid & (g.vpr - 1); r0 = tid >> g.shift; rpp = kThreads >> g.shift; }
+    else { c = tid % g.vpr; r0 = tid / g.vpr; rpp = kThreads / g.vpr; }
+}
+
+template <int DT, int UNROLL>
+__global__ void __launch_bounds__(kThreads) absmax_rows_kernel(const char* __restrict__ x, RowGeom g,
+                                                               uint32_t* __restrict__ absmax_bits) {
+    __shared__ uint32_t red[kThreads / 32];
+    int c, r0, rpp;
+    split_thread(g, threadIdx.x, c, r0, rpp);
+    uint32_t m = 0;
+    if (r0 < rpp) {
+        const int64_t tile = (int64_t)rpp * UNROLL;
+        for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
+            int64_t xo, qo;
+            plane_offsets(g, p, xo, qo);
+            const char* base = x + xo + (int64_t)c * 16;
+            for (int64_t t0 = (int64_t)blockIdx.x * tile + r0; t0 < g.T; t0 += (int64_t)gridDim.x * tile) {
+                uint4 v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int64_t t = t0 + (int64_t)u * rpp;
+                    v[u] = t < g.T ? ld_stream(base + t * g.xT) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
+            }
+        }
+    }
+    m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+    if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits, m);
+}
 
 template <int DT, int BITS, int UNROLL>
-__global__ void __launch_bounds__(kThreads) quant_rows_kernel(const void* __restrict__ x, RowGeom g,
+__global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __restrict__ x, RowGeom g,
                                                               const uint32_t* __restrict__ absmax_bits,
-                                                              int per_token, float eps, void* __restrict__ q,
+                                                              int per_token, float eps, char* __restrict__ q,
                                                               void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out) {
-    const int c = threadIdx.x % g.ipr, r0 = threadIdx.x / g.ipr, rpp = kThreads / g.ipr;
-    constexpr int kOutBytes = BITS == 8 ? 16 : 8;  // bytes of codes per item
-    if (r0 >= rpp) return;
+    constexpr int kOut = OutBytes<DT, BITS>::value;
+    __shared__ float2 tile_scale[kThreads * UNROLL];  // per-token scales of the current tile (s, y)
+    int c, r0, rpp;
+    split_thread(g, threadIdx.x, c, r0, rpp);
+    const bool active = r0 < rpp;
     Scale sc = scale_from_bits<BITS>(per_token ? 0u : absmax_bits[0], eps);
     if (!per_token && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         if (scale_out) store_scalar<DT>(scale_out, 0, sc.s);
         if (scale_f32_out) scale_f32_out[0] = round_through<DT>(sc.s);
     }
-    for (int64_t p = blockIdx.y; p < g.nP; p += gridDim.y) {
-        int64_t xo, qo;
-        plane_offsets(g, p, xo, qo);
-        const char* xin = reinterpret_cast<const char*>(x) + (xo + (int64_t)c * 16) * ElemT<DT>::kSize;
-        char* qout = reinterpret_cast<char*>(q) + qo + (int64_t)c * kOutBytes;
-        const int64_t t0 = (int64_t)blockIdx.x * rpp * UNROLL + r0;
-        Item16<DT> it[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t t = t0 + (int64_t)u * rpp;
-            if (t < g.T) it[u].load(xin + t * g.xT * ElemT<DT>::kSize);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t t = t0 + (int64_t)u * rpp;
-            if (t >= g.T) continue;
-            if (per_token) {
-                sc = scale_from_bits<BITS>(absmax_bits[t], eps);
-                if (p == 0 && c == 0) {
-                    if (scale_out) store_scalar<DT>(scale_out, t, sc.s);
-                    if (scale_f32_out) scale_f32_out[t] = round_through<DT>(sc.s);
+    const int tile = rpp * UNROLL;
+    for (int64_t tb = (int64_t)blockIdx.x * tile; tb < g.T; tb += (int64_t)gridDim.x * tile) {
+        if (per_token) {
+            __syncthreads();  // previous tile's readers are done
+            for (int i = threadIdx.x; i < tile; i += kThreads) {
+                const int64_t t = tb + i;
+                if (t < g.T) {
+                    const Scale s1 = scale_from_bits<BITS>(absmax_bits[t], eps);
+                    tile_scale[i] = make_float2(s1.s, s1.y);
+                    if (blockIdx.y == 0) {
+                        if (scale_out) store_scalar<DT>(scale_out, t, s1.s);
+                        if (scale_f32_out) scale_f32_out[t] = round_through<DT>(s1.s);
+                    }
                 }
             }
-            if (BITS == 8) st_stream(qout + t * g.qT, it[u].quant8(sc));
-            else st_stream8(qout + t * g.qT, it[u].quant4(sc));
+            __syncthreads();
+        }
+        if (!active) continue;
+        for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
+            int64_t xo, qo;
+            plane_offsets(g, p, xo, qo);
+            const char* xin = x + xo + (int64_t)c * 16;
+            char* qout = q + qo + (int64_t)c * kOut;
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t t = tb + r0 + u * rpp;
+                if (t < g.T) v[u] = ld_stream(xin + t * g.xT);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t t = tb + r0 + u * rpp;
+                if (t >= g.T) continue;
+                if (per_token) { const float2 s2 = tile_scale[r0 + u * rpp]; sc.s = s2.x; sc.y = s2.y; }
+                quant_store<DT, BITS>(v[u], sc, qout + t * g.qT);
+            }
         }
     }
 }
 
 // ---- single pass per token: one CTA owns token t across all planes -----------------------------------
-// NI > 0: the token (nP * ipr items) is held in registers, NI items per thread: one HBM read.
-// NI == 0: any size; two loops over the token, the second one hits L2.
+// NV > 0: the token (nP * vpr vectors) is held in registers, NV vectors per thread: one HBM read.
+// NV == 0: any size; two loops over the token, the second one hits L2.
 // MODE 0: quantize (+ scales, + absmax out); MODE 1: absmax only (phase 1 of the head-sharded path).
 
-template <int DT, int BITS, int NI, int MODE>
-__global__ void __launch_bounds__(kThreads) token_fused_kernel(const void* __restrict__ x, RowGeom g, float eps,
-                                                              void* __restrict__ q, void* __restrict__ scale_out,
+template <int DT, int BITS, int NV, int MODE>
+__global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __restrict__ x, RowGeom g, float eps,
+                                                              char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out,
                                                               uint32_t* __restrict__ absmax_out, int accumulate) {
     __shared__ uint32_t red[kThreads / 32];
-    constexpr int kOutBytes = BITS == 8 ? 16 : 8;
-    constexpr int kNI = NI > 0 ? NI : 1;
-    const int64_t t = blockIdx.x;
-    const int items = (int)g.nP * g.ipr;
-    const char* xt = reinterpret_cast<const char*>(x) + t * g.xT * ElemT<DT>::kSize;
-    char* qt = reinterpret_cast<char*>(q) + t * g.qT;
+    constexpr int kOut = OutBytes<DT, BITS>::value;
+    constexpr int kNV = NV > 0 ? NV : 1;
+    const int n_vec = g.nP * g.vpr;
 
-    Item16<DT> it[kNI];
-    int64_t qoff[kNI];
-    uint32_t m = 0;
-    if (NI > 0) {
+    // per-thread vector -> (plane, column) offsets do not depend on the token: compute them once
+    // (32-bit byte offsets: the host only picks NV > 0 when they fit)
+    constexpr uint32_t kNone = 0xffffffffu;
+    uint32_t xoff[kNV], qoff[kNV];
+    if (NV > 0) {
 #pragma unroll
-        for (int k = 0; k < kNI; ++k) {
+        for (int k = 0; k < kNV; ++k) {
             const int j = threadIdx.x + k * kThreads;
-            qoff[k] = -1;
-            if (j < items) {
-                const int p = j / g.ipr, c = j - p * g.ipr;
+            xoff[k] = kNone; qoff[k] = 0;
+            if (j < n_vec) {
+                const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
                 int64_t xo, qo;
                 plane_offsets(g, p, xo, qo);
-                it[k].load(xt + (xo + (int64_t)c * 16) * ElemT<DT>::kSize);
-                qoff[k] = qo + (int64_t)c * kOutBytes;
-            } else {
-                it[k].zero();
+                xoff[k] = (uint32_t)(xo + (int64_t)c * 16);
+                qoff[k] = (uint32_t)(qo + (int64_t)c * kOut);
             }
         }
+    }
+    for (int64_t t = blockIdx.x; t < g.T; t += gridDim.x) {
+        const char* xt = x + t * g.xT;
+        char* qt = q + t * g.qT;
+        uint4 v[kNV];
+        uint32_t m = 0;
+        if (NV > 0) {
 #pragma unroll
-        for (int k = 0; k < kNI; ++k) m = max(m, it[k].absmax_bits());
-    } else {
-        for (int j = threadIdx.x; j < items; j += kThreads) {
-            const int p = j / g.ipr, c = j - p * g.ipr;
-            int64_t xo, qo;
-            plane_offsets(g, p, xo, qo);
-            it[0].load(xt + (xo + (int64_t)c * 16) * ElemT<DT>::kSize);
-            m = max(m, it[0].absmax_bits());
-        }
-    }
-    m = block_max_u32<kThreads>(m, red);
-    if (threadIdx.x == 0 && absmax_out) {
-        if (accumulate) atomicMax(absmax_out + t, m); else absmax_out[t] = m;
-    }
-    if (MODE == 1) return;
-
-    const Scale sc = scale_from_bits<BITS>(m, eps);
-    if (threadIdx.x == 0) {
-        if (scale_out) store_scalar<DT>(scale_out, t, sc.s);
-        if (scale_f32_out) scale_f32_out[t] = round_through<DT>(sc.s);
-    }
-    if (NI > 0) {
+            for (int k = 0; k < kNV; ++k) v[k] = xoff[k] != kNone ? ld_stream(xt + xoff[k]) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int k = 0; k < kNI; ++k) {
-            if (qoff[k] < 0) continue;
-            if (BITS == 8) st_stream(qt + qoff[k], it[k].quant8(sc));
-            else st_stream8(qt + qoff[k], it[k].quant4(sc));
+            for (int k = 0; k < kNV; ++k) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[k]));
+        } else {
+            for (int j = threadIdx.x; j < n_vec; j += kThreads) {
+                const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
+                int64_t xo, qo;
+                plane_offsets(g, p, xo, qo);
+                m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(ld_stream(xt + xo + (int64_t)c * 16)));
+            }
         }
-    } else {
-        for (int j = threadIdx.x; j < items; j += kThreads) {
-            const int p = j / g.ipr, c = j - p * g.ipr;
-            int64_t xo, qo;
-            plane_offsets(g, p, xo, qo);
-            it[0].load(xt + (xo + (int64_t)c * 16) * ElemT<DT>::kSize);
-            if (BITS == 8) st_stream(qt + qo + (int64_t)c * kOutBytes, it[0].quant8(sc));
-            else st_stream8(qt + qo + (int64_t)c * kOutBytes, it[0].quant4(sc));
+        m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+        if (threadIdx.x == 0 && absmax_out) {
+            if (accumulate) atomicMax(absmax_out + t, m); else absmax_out[t] = m;
         }
+        if (MODE == 0) {
+            const Scale sc = scale_from_bits<BITS>(m, eps);
+            if (threadIdx.x == 0) {
+                if (scale_out) store_scalar<DT>(scale_out, t, sc.s);
+                if (scale_f32_out) scale_f32_out[t] = round_through<DT>(sc.s);
+            }
+            if (NV > 0) {
+#pragma unroll
+                for (int k = 0; k < kNV; ++k)
+                    if (xoff[k] != kNone) quant_store<DT, BITS>(v[k], sc, qt + qoff[k]);
+            } else {
+                for (int j = threadIdx.x; j < n_vec; j += kThreads) {
+                    const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
+                    int64_t xo, qo;
+                    plane_offsets(g, p, xo, qo);
+                    quant_store<DT, BITS>(ld_stream(xt + xo + (int64_t)c * 16), sc, qt + qo + (int64_t)c * kOut);
+                }
+            }
+        }
+        __syncthreads();  // `red` is reused by the next token
     }
 }
 
@@ -339,86 +400,103 @@ __global__ void __launch_bounds__(kThreads) quant_generic_kernel(const void* __r
     }
 }
 
-// ---- dequantize ----------------------------------------------------------------------------------------
+// ---- dequantize: the unit is one 16-byte OUTPUT vector (8 fp16/bf16 or 4 fp32 values) --------------------------
 
-// 16 codes -> 16 floats
-template <int BITS> struct Codes16;
-template <> struct Codes16<8> {
-    uint4 v;
-    __device__ __forceinline__ void load(const void* p) { v = ld_stream(p); }
-    __device__ __forceinline__ void to_float(float f[16], float s) const {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[4 * i + k] = __fmul_rn((float)(int)(int8_t)((w[i] >> (8 * k)) & 0xffu), s);
-        }
-    }
-};
-template <> struct Codes16<4> {
-    uint2 v;
-    __device__ __forceinline__ void load(const void* p) { v = ld_stream8(p); }
-    __device__ __forceinline__ void to_float(float f[16], float s) const {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t byte = (w[i] >> (8 * k)) & 0xffu;
-                f[8 * i + 2 * k] = __fmul_rn((float)((int)(byte >> 4) - 8), s);
-                f[8 * i + 2 * k + 1] = __fmul_rn((float)((int)(byte & 0xfu) - 8), s);
-            }
-        }
-    }
+template <int ODT, int BITS> struct CodeIn {
+    static constexpr int kN = 16 / ElemT<ODT>::kSize;   // output elements per vector
+    static constexpr int kBytes = kN * BITS / 8;        // code bytes feeding it: 8, 4 or 2
 };
 
-template <int ODT> __device__ __forceinline__ void store16(void* p, const float f[16]) {
-    if (ODT == KVQ_F32) {
+template <int BYTES> struct Raw;
+template <> struct Raw<8> { uint2 v; __device__ __forceinline__ void load(const void* p) { v = ld_stream8(p); } };
+template <> struct Raw<4> { uint32_t v; __device__ __forceinline__ void load(const void* p) { v = __ldg(reinterpret_cast<const uint32_t*>(p)); } };
+template <> struct Raw<2> { uint32_t v; __device__ __forceinline__ void load(const void* p) { v = __ldg(reinterpret_cast<const unsigned short*>(p)); } };
+
+__device__ __forceinline__ float code8(uint32_t w, int k) { return (float)(int)(int8_t)((w >> (8 * k)) & 0xffu); }
+__device__ __forceinline__ float code4(uint32_t w, int e) {  // element e of the word: byte e/2, even -> high nibble
+    return (float)((int)((w >> (8 * (e >> 1) + ((e & 1) ? 0 : 4))) & 0xfu) - 8);
+}
+
+template <int ODT, int BITS>
+__device__ __forceinline__ void dequant_store(const Raw<CodeIn<ODT, BITS>::kBytes>& r, float s, void* out) {
+    constexpr int kN = CodeIn<ODT, BITS>::kN;
+    float f[kN];
+    if constexpr (BITS == 8) {
+        if constexpr (kN == 8) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&r.v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            st_stream(reinterpret_cast<uint4*>(p) + i, make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
-                                                                  __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3])));
+            for (int i = 0; i < 8; ++i) f[i] = __fmul_rn(code8(w[i >> 2], i & 3), s);
+        } else {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(&r.v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[i] = __fmul_rn(code8(w, i), s);
+        }
     } else {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(&r.v);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-            st_stream(reinterpret_cast<uint4*>(p) + i,
-                      make_uint4(narrow2<ODT>(f[8 * i], f[8 * i + 1]), narrow2<ODT>(f[8 * i + 2], f[8 * i + 3]),
-                                 narrow2<ODT>(f[8 * i + 4], f[8 * i + 5]), narrow2<ODT>(f[8 * i + 6], f[8 * i + 7])));
+        for (int i = 0; i < kN; ++i) f[i] = __fmul_rn(code4(w, i), s);
+    }
+    if constexpr (ODT == KVQ_F32)
+        st_stream(out, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+    else
+        st_stream(out, make_uint4(narrow2<ODT>(f[0], f[1]), narrow2<ODT>(f[2], f[3]), narrow2<ODT>(f[4 % kN], f[5 % kN]),
+                                  narrow2<ODT>(f[6 % kN], f[7 % kN])));
+}
+
+template <int ODT, int BITS, int UNROLL>
+__global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __restrict__ codes, int64_t n_vec,
+                                                                const void* __restrict__ scale, int scale_dtype,
+                                                                uint4* __restrict__ out) {
+    constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
+    const float s = load_scale(scale, scale_dtype, 0);
+    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        Raw<kIn> r[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) r[u].load(codes + j * kIn);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) dequant_store<ODT, BITS>(r[u], s, out + j);
+        }
     }
 }
 
-// g.x* describe the CODES (strides in bytes, rows of ipr items), g.q* the OUTPUT (elements, contiguous rows)
+// g.x* describe the CODES (bytes), g.q* the OUTPUT (bytes); vpr = 16-byte OUTPUT vectors per row
 template <int ODT, int BITS, int UNROLL>
-__global__ void __launch_bounds__(kThreads) dequant_rows_kernel(const void* __restrict__ codes, RowGeom g,
+__global__ void __launch_bounds__(kThreads) dequant_rows_kernel(const char* __restrict__ codes, RowGeom g,
                                                                 const void* __restrict__ scale, int scale_dtype,
-                                                                int per_token, void* __restrict__ out) {
-    const int c = threadIdx.x % g.ipr, r0 = threadIdx.x / g.ipr, rpp = kThreads / g.ipr;
-    constexpr int kInBytes = BITS == 8 ? 16 : 8;
+                                                                int per_token, char* __restrict__ out) {
+    constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
+    int c, r0, rpp;
+    split_thread(g, threadIdx.x, c, r0, rpp);
     if (r0 >= rpp) return;
-    float s = per_token ? 0.f : load_scale(scale, scale_dtype, 0);
-    for (int64_t p = blockIdx.y; p < g.nP; p += gridDim.y) {
+    const float s0 = per_token ? 0.f : load_scale(scale, scale_dtype, 0);
+    const int64_t tile = (int64_t)rpp * UNROLL;
+    for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
         int64_t co, oo;
         plane_offsets(g, p, co, oo);
-        const char* cin = reinterpret_cast<const char*>(codes) + co + (int64_t)c * kInBytes;
-        char* o = reinterpret_cast<char*>(out) + (oo + (int64_t)c * 16) * ElemT<ODT>::kSize;
-        const int64_t t0 = (int64_t)blockIdx.x * rpp * UNROLL + r0;
-        Codes16<BITS> it[UNROLL];
-        float sv[UNROLL];
+        const char* cin = codes + co + (int64_t)c * kIn;
+        char* o = out + oo + (int64_t)c * 16;
+        for (int64_t t0 = (int64_t)blockIdx.x * tile + r0; t0 < g.T; t0 += (int64_t)gridDim.x * tile) {
+            Raw<kIn> r[UNROLL];
+            float sv[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t t = t0 + (int64_t)u * rpp;
-            if (t < g.T) {
-                it[u].load(cin + t * g.xT);
-                sv[u] = per_token ? load_scale(scale, scale_dtype, t) : s;
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t t = t0 + (int64_t)u * rpp;
+                if (t < g.T) {
+                    r[u].load(cin + t * g.xT);
+                    sv[u] = per_token ? load_scale(scale, scale_dtype, t) : s0;
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t t = t0 + (int64_t)u * rpp;
-            if (t >= g.T) continue;
-            float f[16];
-            it[u].to_float(f, sv[u]);
-            store16<ODT>(o + t * g.qT * ElemT<ODT>::kSize, f);
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t t = t0 + (int64_t)u * rpp;
+                if (t < g.T) dequant_store<ODT, BITS>(r[u], sv[u], o + t * g.qT);
+            }
         }
     }
 }
@@ -445,36 +523,40 @@ __global__ void __launch_bounds__(kThreads) dequant_generic_kernel(const void* _
 bool fast_input_ok(const void* x, int dtype, const View4& v) {
     const int es = elem_size(dtype);
     auto ok = [&](int64_t s) { return (s * es) % 16 == 0; };
-    return v.sD == 1 && v.D % 16 == 0 && v.D / 16 <= kThreads && aligned16(x) && ok(v.sB) && ok(v.sH) && ok(v.sT) &&
-           v.B * v.H * v.T * v.D > 0;
+    return v.sD == 1 && (v.D * es) % 16 == 0 && v.D * es / 16 <= kThreads && aligned16(x) && ok(v.sB) && ok(v.sH) && ok(v.sT) &&
+           v.B * v.H * v.T * v.D > 0 && v.B * v.H <= 0x7fffffff;
 }
-bool fast_codes_ok(const void* q, const Stride3& s, int bits, int64_t D) {
-    const int a = bits == 8 ? 16 : 8;
-    return D % 16 == 0 && (reinterpret_cast<uintptr_t>(q) % a) == 0 && s.sB % a == 0 && s.sH % a == 0 && s.sT % a == 0;
+// codes side of a quantize: rows of D*bits/8 bytes written in pieces of `piece` bytes
+bool codes_ok(const void* q, const Stride3& s, int piece) {
+    return (reinterpret_cast<uintptr_t>(q) % piece) == 0 && s.sB % piece == 0 && s.sH % piece == 0 && s.sT % piece == 0;
 }
+int ilog2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
 
-// Collapse a view into planes x rows for a kernel whose work is row-independent.
-// If `merge_rows` (per-tensor granularity) and the layouts allow, (B,H,T) become one run of rows.
-RowGeom row_geom(const View4& v, const Stride3& q, int64_t q_row, bool merge_rows) {
+// x: strides in elements of size es; q: strides in bytes (codes) or elements of size qes
+RowGeom row_geom(const View4& v, int es, const Stride3& q, int qes, int vpr) {
     RowGeom g{};
-    g.ipr = (int)(v.D / 16);
-    g.H = v.H; g.nP = v.B * v.H; g.T = v.T;
-    g.xB = v.sB; g.xH = v.sH; g.xT = v.sT;
-    g.qB = q.sB; g.qH = q.sH; g.qT = q.sT;
-    if (merge_rows) {
-        const bool x_hm = v.sH == v.T * v.sT, q_hm = q.sH == v.T * q.sT;
-        const bool x_bm = v.sB == v.H * v.sH, q_bm = q.sB == v.H * q.sH;
-        if (x_hm && q_hm && x_bm && q_bm) { g.nP = 1; g.H = 1; g.T = v.B * v.H * v.T; }
-        else if (x_hm && q_hm) { g.nP = v.B; g.H = 1; g.T = v.H * v.T; }
-    }
-    (void)q_row;
+    g.nP = (int)(v.B * v.H); g.H = (int)v.H; g.T = v.T;
+    g.xB = v.sB * es; g.xH = v.sH * es; g.xT = v.sT * es;
+    g.qB = q.sB * qes; g.qH = q.sH * qes; g.qT = q.sT * qes;
+    g.vpr = vpr; g.shift = ilog2_exact(vpr);
+    if (v.B == 1) { g.H = 1; g.xB = g.xH; g.qB = g.qH; }
+    else if (v.H == 1) { g.H = 1; }
+    else if (v.sB == v.H * v.sH && q.sB == v.H * q.sH) { g.H = 1; g.xB = g.xH; g.qB = g.qH; }  // uniform planes
     return g;
 }
 
 dim3 row_grid(const RowGeom& g, int unroll) {
-    const int rpp = kThreads / g.ipr;
+    const int rpp = kThreads / g.vpr;
     const int64_t tiles = (g.T + (int64_t)rpp * unroll - 1) / ((int64_t)rpp * unroll);
-    return dim3((unsigned)tiles, (unsigned)(g.nP < 65535 ? g.nP : 65535), 1);
+    const unsigned gy = (unsigned)(g.nP < 65535 ? g.nP : 65535);
+    const int64_t want = ((int64_t)sm_count() * 16 + gy - 1) / gy;  // ~16 CTAs per SM in total
+    const int64_t gx = tiles < want ? tiles : want;
+    return dim3((unsigned)(gx > 0 ? gx : 1), gy, 1);
+}
+unsigned flat_grid(int64_t n_vec, int unroll) {
+    const int64_t blocks = (n_vec + (int64_t)kThreads * unroll - 1) / ((int64_t)kThreads * unroll);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
 GenGeom gen_geom(const View4& v, const Stride3& q) {
@@ -500,22 +582,28 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
                  float* scale_f32_out, cudaStream_t st) {
     KVQ_REQUIRE(x && q && absmax_bits && shape && stride, "null pointer");
     KVQ_REQUIRE(granularity == KVQ_PER_TENSOR || granularity == KVQ_PER_TOKEN, "bad granularity %d", granularity);
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     const View4 v = make_view(shape, stride);
     KVQ_REQUIRE(v.B >= 0 && v.H >= 0 && v.T >= 0 && v.D >= 0, "negative shape");
     const int64_t W = BITS == 8 ? v.D : (v.D + 1) / 2;
     const Stride3 qs = make_stride3(q_stride3, v.H, v.T, W);
     const int64_t n = v.B * v.H * v.T * v.D;
     const int per_token = granularity == KVQ_PER_TOKEN;
-    if (n == 0) {
-        // empty tensor: absmax is 0 -> scale = eps; the reference would raise on max() of an empty tensor,
-        // the Python wrapper keeps that behaviour; here only the scale is written.
-        return KVQ_OK;
-    }
-    if (fast_input_ok(x, dtype, v) && fast_codes_ok(q, qs, BITS, v.D)) {
-        const RowGeom g = row_geom(v, qs, W, !per_token);
-        constexpr int U = 2;
+    if (n == 0) return KVQ_OK;  // the Python wrapper raises like torch's max() on an empty tensor
+    const int es = elem_size(dtype);
+    const int piece = (16 / es) * BITS / 8;  // code bytes produced per input vector
+    const bool q_contig = qs.sT == W && qs.sH == v.T * W && qs.sB == v.H * v.T * W;
+    if (!per_token && is_contiguous(v) && q_contig && aligned16(x) && (n * es) % 16 == 0 && v.D % 2 == 0 &&
+        codes_ok(q, qs, piece)) {
+        const int64_t n_vec = n * es / 16;
+        constexpr int U = 4;
+        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
+                                   (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+    } else if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece)) {
+        const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
+        constexpr int U = 4;
         KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U><<<row_grid(g, U), kThreads, 0, st>>>(
-                                   x, g, absmax_bits, per_token, eps, q, scale_out, scale_f32_out));
+                                   (const char*)x, g, absmax_bits, per_token, eps, (char*)q, scale_out, scale_f32_out));
     } else {
         const GenGeom g = gen_geom(v, qs);
         KVQ_DISPATCH_DT(dtype, quant_generic_kernel<DT, BITS><<<gen_grid(v.B * v.H * v.T * W), kThreads, 0, st>>>(
@@ -530,42 +618,55 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
     KVQ_REQUIRE(codes && scale && out && shape, "null pointer");
     KVQ_REQUIRE(granularity == KVQ_PER_TENSOR || granularity == KVQ_PER_TOKEN, "bad granularity %d", granularity);
     KVQ_REQUIRE(scale_dtype >= 0 && scale_dtype <= 2, "bad scale dtype %d", scale_dtype);
+    KVQ_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "bad out dtype %d", out_dtype);
     const int64_t B = shape[0], H = shape[1], T = shape[2], D = shape[3];
     KVQ_REQUIRE(B >= 0 && H >= 0 && T >= 0 && D >= 0, "negative shape");
     const int64_t W = BITS == 8 ? D : (D + 1) / 2;
     const Stride3 cs = make_stride3(q_stride3, H, T, W);
     const int per_token = granularity == KVQ_PER_TOKEN;
-    if (B * H * T * D == 0) return KVQ_OK;
-    const int64_t contig[4] = {H * T * D, T * D, D, 1};
-    const View4 ov = make_view(shape, contig);
-    if (fast_codes_ok(codes, cs, BITS, D) && D / 16 <= kThreads && aligned16(out)) {
-        // geometry: "x" side = codes (bytes), "q" side = output (elements)
-        View4 cv = ov;
+    const int64_t n = B * H * T * D;
+    if (n == 0) return KVQ_OK;
+    const int oes = elem_size(out_dtype);
+    const int piece = (16 / oes) * BITS / 8;  // code bytes consumed per 16-byte output vector
+    const bool c_contig = cs.sT == W && cs.sH == T * W && cs.sB == H * T * W;
+    const bool rows_ok = (D * oes) % 16 == 0 && D * oes / 16 <= kThreads && aligned16(out) && codes_ok(codes, cs, piece) &&
+                         B * H <= 0x7fffffff && (BITS == 8 || D % 2 == 0);
+    if (!per_token && c_contig && rows_ok) {
+        const int64_t n_vec = n * oes / 16;
+        constexpr int U = 4;
+        KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
+                                       (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out));
+    } else if (rows_ok) {
+        const int64_t contig[4] = {H * T * D, T * D, D, 1};
+        View4 cv = make_view(shape, contig);
         cv.sB = cs.sB; cv.sH = cs.sH; cv.sT = cs.sT;
-        RowGeom g = row_geom(cv, Stride3{contig[0], contig[1], contig[2]}, D, !per_token);
-        constexpr int U = 2;
+        const RowGeom g = row_geom(cv, 1, Stride3{contig[0], contig[1], contig[2]}, oes, (int)(D * oes / 16));
+        constexpr int U = 4;
         KVQ_DISPATCH_DT(out_dtype, dequant_rows_kernel<DT, BITS, U><<<row_grid(g, U), kThreads, 0, st>>>(
-                                       codes, g, scale, scale_dtype, per_token, out));
+                                       (const char*)codes, g, scale, scale_dtype, per_token, (char*)out));
     } else {
-        GenGeom g{B, H, T, D, cs.sB, cs.sH, cs.sT, 1, contig[0], contig[1], contig[2]};
-        KVQ_DISPATCH_DT(out_dtype, dequant_generic_kernel<DT, BITS><<<gen_grid(B * H * T * D), kThreads, 0, st>>>(
+        GenGeom g{B, H, T, D, cs.sB, cs.sH, cs.sT, 1, H * T * D, T * D, D};
+        KVQ_DISPATCH_DT(out_dtype, dequant_generic_kernel<DT, BITS><<<gen_grid(n), kThreads, 0, st>>>(
                                        codes, g, scale, scale_dtype, per_token, out));
     }
     return check_launch("dequant");
 }
 
 template <int DT, int BITS, int MODE>
-void launch_token_fused(int ni, unsigned T, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
+void launch_token_fused(int nv, unsigned grid, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
                         void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate) {
-#define KVQ_TF(NI) token_fused_kernel<DT, BITS, NI, MODE><<<T, kThreads, 0, st>>>(x, g, eps, q, scale_out, scale_f32_out, absmax_out, accumulate)
-    if (MODE == 1) { KVQ_TF(0); return; }
-    switch (ni) {
-        case 1: KVQ_TF(1); break;
-        case 2: KVQ_TF(2); break;
-        case 3: case 4: KVQ_TF(4); break;
-        default: KVQ_TF(0); break;
-    }
+#define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate)
+    if (nv <= 1) KVQ_TF(1);
+    else if (nv <= 2) KVQ_TF(2);
+    else if (nv <= 4) KVQ_TF(4);
+    else if (nv <= 8) KVQ_TF(8);
+    else KVQ_TF(0);
 #undef KVQ_TF
+}
+
+unsigned token_grid(int64_t T) {
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (unsigned)(T < cap ? T : cap);
 }
 
 }  // namespace
@@ -577,26 +678,34 @@ extern "C" int kvq_absmax(const void* x, int dtype, const int64_t shape[4], cons
                           uint32_t* absmax_bits, int accumulate, kvq_stream_t stream) {
     KVQ_REQUIRE(x && absmax_bits && shape && stride, "null pointer");
     KVQ_REQUIRE(granularity == KVQ_PER_TENSOR || granularity == KVQ_PER_TOKEN, "bad granularity %d", granularity);
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     cudaStream_t st = (cudaStream_t)stream;
     const View4 v = make_view(shape, stride);
     KVQ_REQUIRE(v.B >= 0 && v.H >= 0 && v.T >= 0 && v.D >= 0, "negative shape");
     const int per_token = granularity == KVQ_PER_TOKEN;
     const int64_t words = per_token ? v.T : 1;
     const int64_t n = v.B * v.H * v.T * v.D;
+    const int es = elem_size(dtype);
     const bool fast = fast_input_ok(x, dtype, v);
     // the per-token fused kernel overwrites (or atomically accumulates); everything else max-accumulates
     if (!accumulate && !(per_token && fast) && words > 0) KVQ_CUDA(cudaMemsetAsync(absmax_bits, 0, words * 4, st));
     if (n == 0) return KVQ_OK;
-    if (fast && per_token && v.B * v.H * (v.D / 16) < (1 << 30)) {
-        RowGeom g = row_geom(v, Stride3{0, 0, 0}, 0, false);
-        KVQ_REQUIRE(v.T <= 0x7fffffff, "T too large");
-        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 1>(0, (unsigned)v.T, st, x, g, 0.f, nullptr, nullptr, nullptr,
+    if (fast && per_token) {
+        const RowGeom g = row_geom(v, es, Stride3{0, 0, 0}, 1, (int)(v.D * es / 16));
+        const int64_t n_vec = v.B * v.H * (v.D * es / 16);
+        int nv = (int)((n_vec + kThreads - 1) / kThreads);
+        const int64_t xmax = ((v.B - 1) * v.sB + (v.H - 1) * v.sH + v.D) * es;
+        if (xmax >= 0xffffffffLL || xmax < 0 || n_vec >= (1 << 30)) nv = 9;
+        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 1>(nv, token_grid(v.T), st, x, g, 0.f, nullptr, nullptr, nullptr,
                                                             absmax_bits, accumulate));
+    } else if (is_contiguous(v) && aligned16(x) && (n * es) % 16 == 0 && !per_token) {
+        const int64_t n_vec = n * es / 16;
+        constexpr int U = 8;
+        KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const uint4*)x, n_vec, absmax_bits));
     } else if (fast) {
-        RowGeom g = row_geom(v, Stride3{v.H * v.T * v.D, v.T * v.D, v.D}, v.D, true);
-        if (!(v.sH == v.T * v.sT && v.sB == v.H * v.sH)) g = row_geom(v, Stride3{0, 0, 0}, 0, false);
-        constexpr int U = 4;
-        KVQ_DISPATCH_DT(dtype, absmax_rows_kernel<DT, U><<<row_grid(g, U), kThreads, 0, st>>>(x, g, absmax_bits));
+        const RowGeom g = row_geom(v, es, Stride3{0, 0, 0}, 1, (int)(v.D * es / 16));
+        constexpr int U = 8;
+        KVQ_DISPATCH_DT(dtype, absmax_rows_kernel<DT, U><<<row_grid(g, U), kThreads, 0, st>>>((const char*)x, g, absmax_bits));
     } else {
         const GenGeom g = gen_geom(v, Stride3{0, 0, 0});
         KVQ_DISPATCH_DT(dtype, absmax_generic_kernel<DT><<<gen_grid(n), kThreads, 0, st>>>(x, g, per_token, absmax_bits));
@@ -624,22 +733,26 @@ extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t
                                          float* scale_f32_out, uint32_t* absmax_bits_out, kvq_stream_t stream) {
     KVQ_REQUIRE(x && q && shape && stride, "null pointer");
     KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4, got %d", bits);
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     cudaStream_t st = (cudaStream_t)stream;
     const View4 v = make_view(shape, stride);
     KVQ_REQUIRE(v.B >= 0 && v.H >= 0 && v.T >= 0 && v.D >= 0, "negative shape");
-    KVQ_REQUIRE(v.T <= 0x7fffffff, "T too large");
     const int64_t W = bits == 8 ? v.D : (v.D + 1) / 2;
     const Stride3 qs = make_stride3(q_stride3, v.H, v.T, W);
     if (v.B * v.H * v.T * v.D == 0) return KVQ_OK;
-    const int64_t items = v.B * v.H * (v.D / 16);
-    if (fast_input_ok(x, dtype, v) && fast_codes_ok(q, qs, bits, v.D) && items < (1 << 30)) {
-        const RowGeom g = row_geom(v, qs, W, false);
-        const int ni = (int)((items + kThreads - 1) / kThreads);
+    const int es = elem_size(dtype);
+    const int piece = (16 / es) * bits / 8;
+    const int64_t n_vec = v.B * v.H * (v.D * es / 16);
+    if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece) && n_vec < (1 << 30) && (bits == 8 || v.D % 2 == 0)) {
+        const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
+        int nv = (int)((n_vec + kThreads - 1) / kThreads);
+        const int64_t xmax = ((v.B - 1) * v.sB + (v.H - 1) * v.sH + v.D) * es, qmaxo = (v.B - 1) * qs.sB + (v.H - 1) * qs.sH + W;
+        if (xmax >= 0xffffffffLL || qmaxo >= 0xffffffffLL || xmax < 0 || qmaxo < 0) nv = 9;  // offsets need 64 bits: two-loop variant
         if (bits == 8) {
-            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(ni, (unsigned)v.T, st, x, g, eps, q, scale_out,
+            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, token_grid(v.T), st, x, g, eps, q, scale_out,
                                                                 scale_f32_out, absmax_bits_out, 0));
         } else {
-            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(ni, (unsigned)v.T, st, x, g, eps, q, scale_out,
+            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, token_grid(v.T), st, x, g, eps, q, scale_out,
                                                                 scale_f32_out, absmax_bits_out, 0));
         }
         return check_launch("quant_per_token_fused");
