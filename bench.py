@@ -114,7 +114,7 @@ def physical_gpu_index(local_rank: int) -> int:
 # ----------------------------------------------------------------------------- CPU reference arm
 
 
-def cpu_reference_sample(cfg, seconds=12.0, T_slice=512):
+def cpu_reference_sample(cfg, seconds=12.0, T_slice=4096):
     """The reference's CPU path (oracle port, OpenMP over all host cores) on a T-slice of the same tensors:
     absmax -> INT4 quantize+pack -> unpack+dequantize to bf16, per tensor.  Returns (GB/s, cores, sample text, passes)."""
     import torch
@@ -293,12 +293,13 @@ def run_c3(args, cfg):
 
     del xs, packed, outs, x0, x  # the e2e leg brings its data from the host
     torch.cuda.empty_cache()
-    e2e = run_e2e(args, cfg, dev, Hl, world)
+    e2e = run_e2e(args, cfg, dev, Hl, world) if not args.skip_e2e else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
+                                                                          "d2h_bytes_per_step": 0, "_ms": 1.0, "_job_bytes": 0.0}
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.skip_cpu:
         gbs, cores, sample, _ = cpu_reference_sample(cfg, seconds=12.0)
         cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    if world > 1:
+    if world > 1 and not args.skip_e2e:
         # aggregate e2e over ranks: bytes of all ranks / max time
         t = torch.tensor([e2e["_ms"]], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -417,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kvq", choices=["kvq", "reference"])
     ap.add_argument("--layers", type=int, default=None, help="override the number of layers (debug only; not a valid bench line)")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline leg")
     args = ap.parse_args()
     cfg = dict(C3)
     if args.layers:

@@ -412,43 +412,113 @@ template <> struct Raw<8> { uint2 v; __device__ __forceinline__ void load(const 
 template <> struct Raw<4> { uint32_t v; __device__ __forceinline__ void load(const void* p) { v = __ldg(reinterpret_cast<const uint32_t*>(p)); } };
 template <> struct Raw<2> { uint32_t v; __device__ __forceinline__ void load(const void* p) { v = __ldg(reinterpret_cast<const unsigned short*>(p)); } };
 
-__device__ __forceinline__ float code8(uint32_t w, int k) { return (float)(int)(int8_t)((w >> (8 * k)) & 0xffu); }
-__device__ __forceinline__ float code4(uint32_t w, int e) {  // element e of the word: byte e/2, even -> high nibble
-    return (float)((int)((w >> (8 * (e >> 1) + ((e & 1) ? 0 : 4))) & 0xfu) - 8);
+// exact integer -> fp32 without the conversion pipe: drop the (biased) byte into the mantissa of 2^23
+__device__ __forceinline__ float code8(uint32_t x /* w ^ 0x80808080 */, int k) {
+    return __fadd_rn(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650 + k)), -8388736.f);  // 2^23 + 128
+}
+__device__ __forceinline__ float code4(uint32_t nib /* nibbles isolated per byte */, int k) {
+    return __fadd_rn(__uint_as_float(__byte_perm(nib, 0x4B000000u, 0x7650 + k)), -8388616.f);  // 2^23 + 8
 }
 
-template <int ODT, int BITS>
-__device__ __forceinline__ void dequant_store(const Raw<CodeIn<ODT, BITS>::kBytes>& r, float s, void* out) {
+// Scale operand of the dequant kernels.  PK (packed) path: out dtype is 16-bit and the scale has that same
+// dtype, so code * scale is ONE exact 16-bit multiply (code and scale are both exactly representable, the
+// product is rounded once, like fp32-multiply-then-round whose fp32 product is exact): two elements per
+// HMUL2 and no fp32 round trip.  General path: fp32 multiply, then one rounding to the out dtype.
+template <bool PK> struct ScaleArg;
+template <> struct ScaleArg<false> {
+    float f;
+    __device__ __forceinline__ void load(const void* p, int dtype, int64_t i) { f = load_scale(p, dtype, i); }
+};
+template <> struct ScaleArg<true> {
+    uint32_t h2;  // the raw 16-bit scale in both halves
+    __device__ __forceinline__ void load(const void* p, int, int64_t i) {
+        h2 = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p) + i) * 0x10001u;
+    }
+};
+
+template <int ODT> __device__ __forceinline__ uint32_t pk_sub_mul(uint32_t biased, uint32_t offset2, uint32_t s2) {
+    if (ODT == KVQ_F16) {
+        const __half2 c = __hsub2(*reinterpret_cast<const __half2*>(&biased), *reinterpret_cast<const __half2*>(&offset2));
+        const __half2 r = __hmul2(c, *reinterpret_cast<const __half2*>(&s2));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+    const __nv_bfloat162 c = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&biased), *reinterpret_cast<const __nv_bfloat162*>(&offset2));
+    const __nv_bfloat162 r = __hmul2(c, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+template <int ODT, int BITS, bool PK>
+__device__ __forceinline__ void dequant_store(const Raw<CodeIn<ODT, BITS>::kBytes>& r, const ScaleArg<PK>& sa, void* out) {
     constexpr int kN = CodeIn<ODT, BITS>::kN;
-    float f[kN];
-    if constexpr (BITS == 8) {
-        if constexpr (kN == 8) {
+    if constexpr (PK) {
+        static_assert(ODT != KVQ_F32, "packed path is 16-bit only");
+        uint32_t o[4];
+        if constexpr (BITS == 4) {
+            // word k = (hi nibble of byte k, lo nibble of byte k) as 16-bit floats MAGIC + nibble
+            constexpr uint32_t magic2 = ODT == KVQ_F16 ? 0x64006400u : 0x43004300u;   // 1024 | 128
+            constexpr uint32_t off2 = ODT == KVQ_F16 ? 0x64086408u : 0x43084308u;     // MAGIC + 8
+            const uint32_t w = r.v, w4 = w >> 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t t = __byte_perm(w4, w, 0x0400 + k + (k << 8));  // [w4.b_k, w4.b0, w.b_k, w4.b0]
+                o[k] = pk_sub_mul<ODT>((t & 0x000f000fu) | magic2, off2, sa.h2);
+            }
+        } else if constexpr (ODT == KVQ_F16) {
+            // byte ^ 0x80 = code + 128 in [1, 255]; 0x6400 | u = 1024 + u exactly
             const uint32_t* w = reinterpret_cast<const uint32_t*>(&r.v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __fmul_rn(code8(w[i >> 2], i & 3), s);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = w[k >> 1] ^ 0x80808080u;
+                const uint32_t t = __byte_perm(x, 0x64646464u, (k & 1) ? 0x4342 : 0x4140);  // [x.b0|2, 0x64, x.b1|3, 0x64]
+                o[k] = pk_sub_mul<ODT>(t, 0x64806480u /* 1152 */, sa.h2);
+            }
         } else {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(&r.v);
+            // bf16 holds 7 mantissa bits: sign-magnitude.  |code| <= 127 -> 0x4300 | a = 128 + a exactly
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&r.v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) f[i] = __fmul_rn(code8(w, i), s);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t wk = w[k >> 1];
+                const uint32_t a = __vabsss4(wk), sg = wk & 0x80808080u;
+                const uint32_t t = __byte_perm(a, 0x43434343u, (k & 1) ? 0x4342 : 0x4140);
+                const uint32_t sgn = __byte_perm(sg, 0u, (k & 1) ? 0x3424 : 0x1404);  // [0, sg.b, 0, sg.b]
+                o[k] = pk_sub_mul<ODT>(t, 0x43004300u /* 128 */, sa.h2) ^ sgn;
+            }
         }
+        st_stream(out, make_uint4(o[0], o[1], o[2], o[3]));
     } else {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(&r.v);
+        const float s = sa.f;
+        float f[kN];
+        if constexpr (BITS == 8) {
+            if constexpr (kN == 8) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&r.v);
+                const uint32_t x0 = w[0] ^ 0x80808080u, x1 = w[1] ^ 0x80808080u;
 #pragma unroll
-        for (int i = 0; i < kN; ++i) f[i] = __fmul_rn(code4(w, i), s);
+                for (int i = 0; i < 4; ++i) { f[i] = __fmul_rn(code8(x0, i), s); f[4 + i] = __fmul_rn(code8(x1, i), s); }
+            } else {
+                const uint32_t x0 = r.v ^ 0x80808080u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[i] = __fmul_rn(code8(x0, i), s);
+            }
+        } else {
+            const uint32_t w = r.v, hi = (w >> 4) & 0x0f0f0f0fu, lo = w & 0x0f0f0f0fu;
+#pragma unroll
+            for (int i = 0; i < kN / 2; ++i) { f[2 * i] = __fmul_rn(code4(hi, i), s); f[2 * i + 1] = __fmul_rn(code4(lo, i), s); }
+        }
+        if constexpr (ODT == KVQ_F32)
+            st_stream(out, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+        else
+            st_stream(out, make_uint4(narrow2<ODT>(f[0], f[1]), narrow2<ODT>(f[2], f[3]), narrow2<ODT>(f[4 % kN], f[5 % kN]),
+                                      narrow2<ODT>(f[6 % kN], f[7 % kN])));
     }
-    if constexpr (ODT == KVQ_F32)
-        st_stream(out, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
-    else
-        st_stream(out, make_uint4(narrow2<ODT>(f[0], f[1]), narrow2<ODT>(f[2], f[3]), narrow2<ODT>(f[4 % kN], f[5 % kN]),
-                                  narrow2<ODT>(f[6 % kN], f[7 % kN])));
 }
 
-template <int ODT, int BITS, int UNROLL>
+template <int ODT, int BITS, bool PK, int UNROLL>
 __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __restrict__ codes, int64_t n_vec,
                                                                 const void* __restrict__ scale, int scale_dtype,
                                                                 uint4* __restrict__ out) {
     constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
-    const float s = load_scale(scale, scale_dtype, 0);
+    ScaleArg<PK> sa;
+    sa.load(scale, scale_dtype, 0);
     const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
     for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
         Raw<kIn> r[UNROLL];
@@ -460,13 +530,13 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __re
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) dequant_store<ODT, BITS>(r[u], s, out + j);
+            if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sa, out + j);
         }
     }
 }
 
 // g.x* describe the CODES (bytes), g.q* the OUTPUT (bytes); vpr = 16-byte OUTPUT vectors per row
-template <int ODT, int BITS, int UNROLL>
+template <int ODT, int BITS, bool PK, int UNROLL>
 __global__ void __launch_bounds__(kThreads) dequant_rows_kernel(const char* __restrict__ codes, RowGeom g,
                                                                 const void* __restrict__ scale, int scale_dtype,
                                                                 int per_token, char* __restrict__ out) {
@@ -474,29 +544,28 @@ __global__ void __launch_bounds__(kThreads) dequant_rows_kernel(const char* __re
     int c, r0, rpp;
     split_thread(g, threadIdx.x, c, r0, rpp);
     if (r0 >= rpp) return;
-    const float s0 = per_token ? 0.f : load_scale(scale, scale_dtype, 0);
+    ScaleArg<PK> s0;
+    s0.load(scale, scale_dtype, 0);
     const int64_t tile = (int64_t)rpp * UNROLL;
+    const int64_t in_step = (int64_t)rpp * g.xT, out_step = (int64_t)rpp * g.qT;
     for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
         int64_t co, oo;
         plane_offsets(g, p, co, oo);
-        const char* cin = codes + co + (int64_t)c * kIn;
-        char* o = out + oo + (int64_t)c * 16;
         for (int64_t t0 = (int64_t)blockIdx.x * tile + r0; t0 < g.T; t0 += (int64_t)gridDim.x * tile) {
+            const char* cin = codes + co + (int64_t)c * kIn + t0 * g.xT;
+            char* o = out + oo + (int64_t)c * 16 + t0 * g.qT;
             Raw<kIn> r[UNROLL];
-            float sv[UNROLL];
+            ScaleArg<PK> sv[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const int64_t t = t0 + (int64_t)u * rpp;
-                if (t < g.T) {
-                    r[u].load(cin + t * g.xT);
-                    sv[u] = per_token ? load_scale(scale, scale_dtype, t) : s0;
+                if (t0 + (int64_t)u * rpp < g.T) {
+                    r[u].load(cin + u * in_step);
+                    if (per_token) sv[u].load(scale, scale_dtype, t0 + (int64_t)u * rpp); else sv[u] = s0;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t t = t0 + (int64_t)u * rpp;
-                if (t < g.T) dequant_store<ODT, BITS>(r[u], sv[u], o + t * g.qT);
-            }
+            for (int u = 0; u < UNROLL; ++u)
+                if (t0 + (int64_t)u * rpp < g.T) dequant_store<ODT, BITS, PK>(r[u], sv[u], o + u * out_step);
         }
     }
 }
@@ -629,21 +698,32 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
     const int oes = elem_size(out_dtype);
     const int piece = (16 / oes) * BITS / 8;  // code bytes consumed per 16-byte output vector
     const bool c_contig = cs.sT == W && cs.sH == T * W && cs.sB == H * T * W;
+    const bool pk = scale_dtype == out_dtype && out_dtype != KVQ_F32 && (reinterpret_cast<uintptr_t>(scale) % 2) == 0;
     const bool rows_ok = (D * oes) % 16 == 0 && D * oes / 16 <= kThreads && aligned16(out) && codes_ok(codes, cs, piece) &&
                          B * H <= 0x7fffffff && (BITS == 8 || D % 2 == 0);
     if (!per_token && c_contig && rows_ok) {
         const int64_t n_vec = n * oes / 16;
         constexpr int U = 4;
-        KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
-                                       (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out));
+        if (pk) {
+            if (out_dtype == KVQ_F16) dequant_flat_kernel<KVQ_F16, BITS, true, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out);
+            else dequant_flat_kernel<KVQ_BF16, BITS, true, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out);
+        } else {
+            KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, false, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
+                                           (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out));
+        }
     } else if (rows_ok) {
         const int64_t contig[4] = {H * T * D, T * D, D, 1};
         View4 cv = make_view(shape, contig);
         cv.sB = cs.sB; cv.sH = cs.sH; cv.sT = cs.sT;
         const RowGeom g = row_geom(cv, 1, Stride3{contig[0], contig[1], contig[2]}, oes, (int)(D * oes / 16));
         constexpr int U = 4;
-        KVQ_DISPATCH_DT(out_dtype, dequant_rows_kernel<DT, BITS, U><<<row_grid(g, U), kThreads, 0, st>>>(
-                                       (const char*)codes, g, scale, scale_dtype, per_token, (char*)out));
+        if (pk) {
+            if (out_dtype == KVQ_F16) dequant_rows_kernel<KVQ_F16, BITS, true, U><<<row_grid(g, U), kThreads, 0, st>>>((const char*)codes, g, scale, scale_dtype, per_token, (char*)out);
+            else dequant_rows_kernel<KVQ_BF16, BITS, true, U><<<row_grid(g, U), kThreads, 0, st>>>((const char*)codes, g, scale, scale_dtype, per_token, (char*)out);
+        } else {
+            KVQ_DISPATCH_DT(out_dtype, dequant_rows_kernel<DT, BITS, false, U><<<row_grid(g, U), kThreads, 0, st>>>(
+                                           (const char*)codes, g, scale, scale_dtype, per_token, (char*)out));
+        }
     } else {
         GenGeom g{B, H, T, D, cs.sB, cs.sH, cs.sT, 1, H * T * D, T * D, D};
         KVQ_DISPATCH_DT(out_dtype, dequant_generic_kernel<DT, BITS><<<gen_grid(n), kThreads, 0, st>>>(

@@ -107,6 +107,22 @@ def test_edge_inputs(kvq):
     assert out.tolist() == [0.5, -1.0]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_dequant_packed_path_corner_cases(kvq, oracle, dtype):
+    """The 16-bit dequant path multiplies code * scale in half precision (exact operands, one rounding).
+    Sweep every code against scales that hit subnormal / tiny / huge products and mismatched scale dtypes."""
+    codes8 = torch.arange(-127, 128, dtype=torch.int8).repeat(2)[:496].reshape(1, 1, 31, 16)
+    nib = torch.arange(0, 256, dtype=torch.uint8).repeat(2)[:496].reshape(1, 1, 31, 16)
+    for sval in (0.0, 6e-8, 1.2e-7, 3.1e-5, 0.007, 0.33, 1.0, 3.0, 511.0, 6.5e4 / 127):
+        for sdt in (dtype, torch.float32):
+            s = torch.tensor(sval, dtype=sdt)
+            for odt in (dtype, torch.float32):
+                got = kvq.dequantize_int8_per_tensor(codes8.cuda(), s.cuda(), odt)
+                assert bits_equal(got.cpu(), oracle.dequantize_int8_per_tensor(codes8, s, odt)), (sval, sdt, odt)
+                got = kvq.dequantize_int4_per_tensor_packed(nib.cuda(), s.cuda(), 32, odt)
+                assert bits_equal(got.cpu(), oracle.dequantize_int4_per_tensor_packed(nib, s, 32, odt)), (sval, sdt, odt)
+
+
 def test_kvq_ext_facade(kvq, oracle):
     ext = kvq.get_cuda_extension()
     q = torch.randint(-127, 128, (3, 5, 16), dtype=torch.int8)
