@@ -101,30 +101,40 @@ struct CopyGeom {
     int64_t sB, sH, sT;   // source strides in BYTES
     int64_t dB, dH, dT;   // destination strides in BYTES
     int cpr;              // 16-byte chunks per row
+    int shift;            // log2(cpr) when it is a power of two, else -1
 };
 
-// dst[p, j, :] = src[p, src_token(j), :]; a thread moves UNROLL 16-byte chunks (same chunk column of
-// UNROLL different rows), all loads issued before the first store.
+// dst[p, j, :] = src[p, src_token(j), :].  A CTA owns a tile of destination rows: their source tokens are
+// evaluated once (one thread per row) into shared memory and reused for every plane (b, h) the CTA walks,
+// so the copy loop is LDS + two address IMADs + LDG.128 + STG.128 per 16 bytes, UNROLL loads in flight.
 template <int UNROLL>
 __global__ void __launch_bounds__(kThreads) evict_gather_kernel(const char* __restrict__ src, char* __restrict__ dst,
                                                                CopyGeom g, PlanDev pl, const int32_t* __restrict__ table) {
-    const int c = threadIdx.x % g.cpr, r0 = threadIdx.x / g.cpr, rpp = kThreads / g.cpr;
-    if (r0 >= rpp) return;
-    for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
-        const int b = p / g.H, h = p - b * g.H;
-        const char* s = src + b * g.sB + h * g.sH + (int64_t)c * 16;
-        char* d = dst + b * g.dB + h * g.dH + (int64_t)c * 16;
-        const int j0 = blockIdx.x * rpp * UNROLL + r0;
-        uint4 v[UNROLL];
+    __shared__ int src_row[kThreads * UNROLL];
+    int c, r0, rpp;
+    if (g.shift >= 0) { c = threadIdx.x & (g.cpr - 1); r0 = threadIdx.x >> g.shift; rpp = kThreads >> g.shift; }
+    else { c = threadIdx.x % g.cpr; r0 = threadIdx.x / g.cpr; rpp = kThreads / g.cpr; }
+    const bool active = r0 < rpp;
+    const int tile = rpp * UNROLL;
+    for (int j0 = blockIdx.x * tile; j0 < pl.n_total; j0 += gridDim.x * tile) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < tile; i += kThreads) src_row[i] = j0 + i < pl.n_total ? src_token(pl, j0 + i, table) : -1;
+        __syncthreads();
+        if (!active) continue;
+        int st[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int j = j0 + u * rpp;
-            if (j < pl.n_total) v[u] = ld_stream(s + (int64_t)src_token(pl, j, table) * g.sT);
-        }
+        for (int u = 0; u < UNROLL; ++u) st[u] = src_row[r0 + u * rpp];
+        for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
+            const int b = g.H == 1 ? p : p / g.H, h = p - b * g.H;
+            const char* s = src + b * g.sB + h * g.sH + (int64_t)c * 16;
+            char* d = dst + b * g.dB + h * g.dH + (int64_t)c * 16 + (int64_t)(j0 + r0) * g.dT;
+            uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int j = j0 + u * rpp;
-            if (j < pl.n_total) st_stream(d + (int64_t)j * g.dT, v[u]);
+            for (int u = 0; u < UNROLL; ++u)
+                if (st[u] >= 0) v[u] = ld_stream(s + (int64_t)st[u] * g.sT);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                if (st[u] >= 0) st_stream(d + (int64_t)(u * rpp) * g.dT, v[u]);
         }
     }
 }
@@ -329,10 +339,18 @@ extern "C" int kvq_evict_gather(const void* src, int elem_bytes, const int64_t s
                       a16(stride[1]) && a16(stride[2]) && a16(ds.sB) && a16(ds.sH) && a16(ds.sT) && B * H <= 0x7fffffff;
     if (fast) {
         CopyGeom g{(int)(B * H), (int)H, stride[0] * elem_bytes, stride[1] * elem_bytes, stride[2] * elem_bytes,
-                   ds.sB * elem_bytes, ds.sH * elem_bytes, ds.sT * elem_bytes, (int)(rb / 16)};
+                   ds.sB * elem_bytes, ds.sH * elem_bytes, ds.sT * elem_bytes, (int)(rb / 16), -1};
+        for (int sft = 0; sft < 9; ++sft) if ((1 << sft) == g.cpr) g.shift = sft;
+        if (B == 1) { g.H = 1; g.sB = g.sH; g.dB = g.dH; }
+        else if (H == 1) { g.H = 1; }
+        else if (stride[0] == H * stride[1] && ds.sB == H * ds.sH) { g.H = 1; g.sB = g.sH; g.dB = g.dH; }  // uniform planes
         constexpr int U = 4;
         const int rpp = kThreads / g.cpr;
-        dim3 grid((unsigned)((n_out + (int64_t)rpp * U - 1) / ((int64_t)rpp * U)), (unsigned)(g.nP < 65535 ? g.nP : 65535));
+        const int64_t tiles = (n_out + (int64_t)rpp * U - 1) / ((int64_t)rpp * U);
+        const int64_t total = (int64_t)sm_count() * 16;
+        int64_t gx = tiles < total ? tiles : total, gy = (total + gx - 1) / gx;
+        if (gy > g.nP) gy = g.nP;
+        dim3 grid((unsigned)gx, (unsigned)(gy > 0 ? gy : 1));
         evict_gather_kernel<U><<<grid, kThreads, 0, st>>>((const char*)src, (char*)dst, g, pd, old_table);
     } else {
         const unsigned grid = gen_grid(B * H * n_out * D);

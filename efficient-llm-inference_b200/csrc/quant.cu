@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __rest
                                                               void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out) {
     constexpr int kOut = OutBytes<DT, BITS>::value;
-    __shared__ float2 tile_scale[kThreads * UNROLL];  // per-token scales of the current tile (s, y)
+    __shared__ float2 tile_scale[kThreads * UNROLL];  // per-token (s, y) of the current tile
     int c, r0, rpp;
     split_thread(g, threadIdx.x, c, r0, rpp);
     const bool active = r0 < rpp;
@@ -231,40 +231,44 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __rest
         if (scale_f32_out) scale_f32_out[0] = round_through<DT>(sc.s);
     }
     const int tile = rpp * UNROLL;
+    const int64_t in_step = (int64_t)rpp * g.xT, out_step = (int64_t)rpp * g.qT;
     for (int64_t tb = (int64_t)blockIdx.x * tile; tb < g.T; tb += (int64_t)gridDim.x * tile) {
-        if (per_token) {
-            __syncthreads();  // previous tile's readers are done
-            for (int i = threadIdx.x; i < tile; i += kThreads) {
-                const int64_t t = tb + i;
-                if (t < g.T) {
-                    const Scale s1 = scale_from_bits<BITS>(absmax_bits[t], eps);
-                    tile_scale[i] = make_float2(s1.s, s1.y);
-                    if (blockIdx.y == 0) {
-                        if (scale_out) store_scalar<DT>(scale_out, t, s1.s);
-                        if (scale_f32_out) scale_f32_out[t] = round_through<DT>(s1.s);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (!active) continue;
+        bool first = true;
         for (int p = blockIdx.y; p < g.nP; p += gridDim.y) {
+            // issue this plane's loads before anything that waits (the scale words, the barrier)
             int64_t xo, qo;
             plane_offsets(g, p, xo, qo);
-            const char* xin = x + xo + (int64_t)c * 16;
-            char* qout = q + qo + (int64_t)c * kOut;
+            const char* xin = x + xo + (int64_t)c * 16 + (tb + r0) * g.xT;
+            char* qout = q + qo + (int64_t)c * kOut + (tb + r0) * g.qT;
             uint4 v[UNROLL];
+            if (active) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t t = tb + r0 + u * rpp;
-                if (t < g.T) v[u] = ld_stream(xin + t * g.xT);
+                for (int u = 0; u < UNROLL; ++u)
+                    if (tb + r0 + u * rpp < g.T) v[u] = ld_stream(xin + u * in_step);
             }
+            if (per_token && first) {  // once per tile: the tokens' scales, shared by every plane
+                __syncthreads();       // readers of the previous tile are done
+                for (int i = threadIdx.x; i < tile; i += kThreads) {
+                    const int64_t t = tb + i;
+                    if (t < g.T) {
+                        const Scale s1 = scale_from_bits<BITS>(absmax_bits[t], eps);
+                        tile_scale[i] = make_float2(s1.s, s1.y);
+                        if (blockIdx.y == 0) {
+                            if (scale_out) store_scalar<DT>(scale_out, t, s1.s);
+                            if (scale_f32_out) scale_f32_out[t] = round_through<DT>(s1.s);
+                        }
+                    }
+                }
+                __syncthreads();
+                first = false;
+            }
+            if (active) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t t = tb + r0 + u * rpp;
-                if (t >= g.T) continue;
-                if (per_token) { const float2 s2 = tile_scale[r0 + u * rpp]; sc.s = s2.x; sc.y = s2.y; }
-                quant_store<DT, BITS>(v[u], sc, qout + t * g.qT);
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (tb + r0 + u * rpp >= g.T) continue;
+                    if (per_token) { const float2 s2 = tile_scale[r0 + u * rpp]; sc.s = s2.x; sc.y = s2.y; }
+                    quant_store<DT, BITS>(v[u], sc, qout + u * out_step);
+                }
             }
         }
     }
@@ -614,6 +618,18 @@ RowGeom row_geom(const View4& v, int es, const Stride3& q, int qes, int vpr) {
     return g;
 }
 
+// planes are looped inside the CTA (the per-tile scales are reused): y covers at most 8 plane groups
+dim3 row_grid_planes_inside(const RowGeom& g, int unroll) {
+    const int rpp = kThreads / g.vpr;
+    const int64_t tiles = (g.T + (int64_t)rpp * unroll - 1) / ((int64_t)rpp * unroll);
+    const int64_t total = (int64_t)sm_count() * 16;
+    int64_t gx = tiles < total ? tiles : total;
+    int64_t gy = (total + gx - 1) / gx;
+    if (gy > g.nP) gy = g.nP;
+    if (gy > 65535) gy = 65535;
+    return dim3((unsigned)(gx > 0 ? gx : 1), (unsigned)(gy > 0 ? gy : 1), 1);
+}
+
 dim3 row_grid(const RowGeom& g, int unroll) {
     const int rpp = kThreads / g.vpr;
     const int64_t tiles = (g.T + (int64_t)rpp * unroll - 1) / ((int64_t)rpp * unroll);
@@ -671,7 +687,7 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
     } else if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece)) {
         const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
         constexpr int U = 4;
-        KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U><<<row_grid(g, U), kThreads, 0, st>>>(
+        KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U><<<row_grid_planes_inside(g, U), kThreads, 0, st>>>(
                                    (const char*)x, g, absmax_bits, per_token, eps, (char*)q, scale_out, scale_f32_out));
     } else {
         const GenGeom g = gen_geom(v, qs);
