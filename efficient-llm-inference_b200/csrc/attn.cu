@@ -16,6 +16,7 @@
 //              memory once per split.
 // Partials (m, l, acc[D]) per (b, hq, split) go to the workspace; a second kernel merges the splits.
 #include <cmath>
+#include <cstdlib>
 
 #include "kvq_common.cuh"
 
@@ -260,6 +261,281 @@ __global__ void __launch_bounds__(kThreads) decode_attn_split_kernel(AttnParams 
     }
 }
 
+// =====================================================================================================
+// TMA-pipelined variant (used whenever the code rows of a (b, h) plane are contiguous, i.e. always for the
+// cache store of this package).  The split-K loop is latency-bound when every tile's loads are issued only
+// after the previous tile's math: here one elected thread streams tiles of 128 tokens -- K codes, V codes and
+// both scale vectors -- into a ring of shared-memory stages with cp.async.bulk (the TMA bulk-copy engine,
+// SASS UBLKCP) completing on an mbarrier per stage, 2-3 tiles ahead of the math.  All 256 threads are
+// consumers; the softmax bookkeeping is folded into the two math phases (per-warp maxima during the K phase,
+// exp2 on the fly in the V phase), so a tile costs two block barriers.
+// =====================================================================================================
+
+#ifndef KVQ_ATTN_RING_KB
+#define KVQ_ATTN_RING_KB 100
+#endif
+#ifndef KVQ_ATTN_CTAS_PER_SM
+#define KVQ_ATTN_CTAS_PER_SM 2
+#endif
+constexpr int kThreads2 = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KBITS, int VBITS, int G, int D> struct TmaCfg {
+    static constexpr int kKRow = D * KBITS / 8, kVRow = D * VBITS / 8;
+    static constexpr int kKTile = kTile * kKRow, kVTile = kTile * kVRow;
+    static constexpr int kStage = kKTile + kVTile;
+    // three CTAs (24 warps) per SM: 3 x (ring + ~1.2 KB of bookkeeping + 1 KB reserved) must fit 227 KB
+    static constexpr int kStagesRaw = (KVQ_ATTN_RING_KB * 1024) / kStage;
+    static constexpr int kStages = kStagesRaw > 4 ? 4 : (kStagesRaw < 2 ? 2 : kStagesRaw);
+    static constexpr int kRed = kThreads2 * 32 * 4;  // final cross-row-group reduction aliases the ring
+    static constexpr int kBuf = kStages * kStage > kRed ? kStages * kStage : kRed;
+    static constexpr int kSmem = kBuf + G * D * 4 + G * kTile * 4 + G * 8 * 4 + G * 4 + kStages * 8 + 16;
+};
+
+template <int BITS, int N> struct SmemCodes {
+    static constexpr int kBytes = N * BITS / 8;
+    static constexpr int kWords = kBytes >= 4 ? kBytes / 4 : 1;
+    uint32_t w[kWords];
+    __device__ __forceinline__ void load(const uint8_t* p) {
+        if constexpr (kBytes == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
+        else if constexpr (kBytes == 4) w[0] = *reinterpret_cast<const uint32_t*>(p);
+        else if constexpr (kBytes == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
+        else {
+#pragma unroll
+            for (int i = 0; i < kBytes / 16; ++i) {
+                const uint4 t = *reinterpret_cast<const uint4*>(p + 16 * i);
+                w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+            }
+        }
+    }
+    __device__ __forceinline__ void to_float(float f[N]) const {
+        if constexpr (BITS == 8) {
+#pragma unroll
+            for (int i = 0; i < N / 4; ++i) int8x4_to_float(w[i], f + 4 * i);
+        } else if constexpr (N >= 8) {
+#pragma unroll
+            for (int i = 0; i < N / 8; ++i) int4x8_to_float(w[i], f + 8 * i);
+        } else {
+            float t[8];
+            int4x8_to_float(w[0], t);
+#pragma unroll
+            for (int i = 0; i < N; ++i) f[i] = t[i];
+        }
+    }
+};
+
+template <int KBITS, int VBITS, int G, int D>
+__global__ void __launch_bounds__(kThreads2) decode_attn_tma_kernel(AttnParams P) {
+    using C = TmaCfg<KBITS, VBITS, G, D>;
+    constexpr int LPR = D / 16, KROWS = kThreads2 / LPR, KPASS = kTile / KROWS;
+    constexpr int EV = 32 / G, LPRV = D / EV, VROWS = kThreads2 / LPRV, VPASS = (kTile + VROWS - 1) / VROWS;
+    constexpr bool kQRegs = G <= 2;
+    constexpr int kWarps = kThreads2 / 32;
+    static_assert(G == 1 || G == 2 || G == 4 || G == 8, "G");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);          // [G][D]
+    float* p_s = q_s + G * D;                                           // [G][kTile] raw scores (log2 domain)
+    float* wmax_s = p_s + G * kTile;                                    // [G][8] per-warp tile maxima
+    float* l_s = wmax_s + G * 8;                                        // [G]
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(l_s + G) + 7) & ~uintptr_t(7));
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t_begin = split * P.tokens_per_split;
+    const int t_end = min(P.T, t_begin + P.tokens_per_split);
+    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
+    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < G * D; i += kThreads2) {
+        const int g = i / D, d = i - g * D;
+        q_s[i] = load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + (int64_t)h * G + g) * D + d) * P.qk_scale_log2;
+    }
+    if (tid < G) l_s[tid] = 0.f;
+    __syncthreads();
+
+    auto issue = [&](int tile_idx) {  // one thread: arm the stage's mbarrier, start the bulk copies
+        const int s = tile_idx % C::kStages;
+        const int t0 = t_begin + tile_idx * kTile;
+        const int rows = min(kTile, t_end - t0);
+        uint8_t* sb = smem_raw + s * C::kStage;
+        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
+        mbar_expect_tx(&full[s], kb + vb);
+        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
+        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < C::kStages - 1 && i < n_tiles; ++i) issue(i);
+    }
+
+    const int kc = tid % LPR, kr = tid / LPR;
+    const int vc = tid % LPRV, vr = tid / LPRV;
+    float qr[kQRegs ? G : 1][16];
+    if (kQRegs) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) qr[g][e] = q_s[g * D + kc * 16 + e];
+    }
+    float acc[G][EV], m_run[G], l_loc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        m_run[g] = -INFINITY; l_loc[g] = 0.f;
+#pragma unroll
+        for (int e = 0; e < EV; ++e) acc[g][e] = 0.f;
+    }
+
+    // per-token scales of the rows this thread touches: plain (L1/L2-resident) loads, fetched one tile ahead
+    float ksn[KPASS], vsn[VPASS];
+    auto fetch_scales = [&](int tile_idx) {
+        const int t0 = t_begin + tile_idx * kTile;
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) { const int t = t0 + ps * KROWS + kr; ksn[ps] = t < t_end ? __ldg(P.k_scale + t) : 0.f; }
+#pragma unroll
+        for (int ps = 0; ps < VPASS; ++ps) { const int t = t0 + ps * VROWS + vr; vsn[ps] = t < t_end ? __ldg(P.v_scale + t) : 0.f; }
+    };
+    fetch_scales(0);
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % C::kStages;
+        if (tid == 0 && it + C::kStages - 1 < n_tiles) issue(it + C::kStages - 1);  // refills the stage released last iteration
+        float ksc[KPASS], vsc[VPASS];
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) ksc[ps] = ksn[ps];
+#pragma unroll
+        for (int ps = 0; ps < VPASS; ++ps) vsc[ps] = vsn[ps];
+        if (it + 1 < n_tiles) fetch_scales(it + 1);
+        while (!mbar_try_wait(&full[s], (it / C::kStages) & 1)) {}
+        const uint8_t* sb = smem_raw + s * C::kStage;
+        const int t0 = t_begin + it * kTile;
+        const int rows = min(kTile, t_end - t0);
+        // ---- K phase: scores (log2 domain) into p_s, per-warp maxima into wmax_s
+        float wm[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) wm[g] = -INFINITY;
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) {
+            const int row = ps * KROWS + kr;
+            SmemCodes<KBITS, 16> kv;
+            kv.load(sb + row * C::kKRow + kc * (16 * KBITS / 8));
+            float f[16];
+            kv.to_float(f);
+            const float sc = ksc[ps];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float d = 0.f;
+                if (kQRegs) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) d = fmaf(qr[g][e], f[e], d);
+                } else {
+                    const float4* qp = reinterpret_cast<const float4*>(&q_s[g * D + kc * 16]);
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 qq = qp[e4];
+                        d = fmaf(qq.x, f[4 * e4], d); d = fmaf(qq.y, f[4 * e4 + 1], d);
+                        d = fmaf(qq.z, f[4 * e4 + 2], d); d = fmaf(qq.w, f[4 * e4 + 3], d);
+                    }
+                }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                const float sv = row < rows ? d * sc : -INFINITY;
+                if (kc == 0) p_s[g * kTile + row] = sv;
+                wm[g] = fmaxf(wm[g], sv);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int o = 16; o >= LPR; o >>= 1) wm[g] = fmaxf(wm[g], __shfl_xor_sync(0xffffffffu, wm[g], o));
+            if (lane == 0) wmax_s[g * 8 + warp] = wm[g];
+        }
+        __syncthreads();
+        // ---- V phase: running max, rescale, exp2 on the fly, accumulate
+        float m_new[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float mt = -INFINITY;
+#pragma unroll
+            for (int w8 = 0; w8 < kWarps; ++w8) mt = fmaxf(mt, wmax_s[g * 8 + w8]);
+            m_new[g] = fmaxf(m_run[g], mt);
+            const float a = m_run[g] == -INFINITY ? 0.f : exp2f(m_run[g] - m_new[g]);
+            m_run[g] = m_new[g];
+            l_loc[g] *= a;
+#pragma unroll
+            for (int e = 0; e < EV; ++e) acc[g][e] *= a;
+        }
+#pragma unroll
+        for (int ps = 0; ps < VPASS; ++ps) {
+            const int row = ps * VROWS + vr;
+            if (VROWS * VPASS > kTile && row >= kTile) break;
+            SmemCodes<VBITS, EV> vv;
+            vv.load(sb + C::kKTile + row * C::kVRow + vc * (EV * VBITS / 8));
+            float f[EV];
+            vv.to_float(f);
+            const float vs = vsc[ps];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float sv = p_s[g * kTile + row];
+                const float pw = sv == -INFINITY ? 0.f : exp2f(sv - m_new[g]);
+                if (vc == 0) l_loc[g] += pw;
+                const float w = pw * vs;
+#pragma unroll
+                for (int e = 0; e < EV; ++e) acc[g][e] = fmaf(w, f[e], acc[g][e]);
+            }
+        }
+        __syncthreads();  // releases stage s, p_s and wmax_s
+    }
+
+    // ---- reduce the row groups through shared memory (aliases the ring: every issued tile was consumed)
+    float* red_s = reinterpret_cast<float*>(smem_raw);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (vc == 0 && vr < kTile) atomicAdd(&l_s[g], l_loc[g]);
+#pragma unroll
+        for (int e = 0; e < EV; ++e) red_s[(vr * G + g) * D + vc * EV + e] = acc[g][e];
+    }
+    __syncthreads();
+    for (int o = tid; o < G * D; o += kThreads2) {
+        float sum = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < VROWS; ++r) sum += red_s[r * G * D + o];
+        const int g = o / D, d = o - g * D;
+        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
+        P.ws_acc[(hq * P.n_splits + split) * D + d] = sum;
+    }
+    if (tid == 0) {  // m_run is identical in every thread
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
+            P.ws_ml[(hq * P.n_splits + split) * 2] = m_run[g];
+            P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = l_s[g];
+        }
+    }
+}
+
 template <int ODT>
 __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
                                          void* __restrict__ out) {
@@ -278,25 +554,45 @@ __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const
     store_scalar<ODT>(out, hq * D + d, num / den);
 }
 
+template <int KBITS, int VBITS, int G, int D>
+int launch_tma(dim3 grid, cudaStream_t st, const AttnParams& P) {
+    using C = TmaCfg<KBITS, VBITS, G, D>;
+    auto kern = decode_attn_tma_kernel<KBITS, VBITS, G, D>;
+    static thread_local int configured_dev = -1;  // per instantiation, per host thread
+    int dev = 0;
+    KVQ_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        configured_dev = dev;
+    }
+    kern<<<grid, kThreads2, C::kSmem, st>>>(P);
+    return KVQ_OK;
+}
+
 template <int KBITS, int VBITS, int G>
-int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P) {
+int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
+    if constexpr (G <= 2) {  // GQA groups of 4 / 8 are FMA-bound: the register-staged variant is faster there
+        if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
+    }
     if (D == 128) decode_attn_split_kernel<KBITS, VBITS, G, 128><<<grid, kThreads, 0, st>>>(P);
     else decode_attn_split_kernel<KBITS, VBITS, G, 64><<<grid, kThreads, 0, st>>>(P);
     return KVQ_OK;
 }
 template <int KBITS, int VBITS>
-int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P) {
+int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
     switch (G) {
-        case 1: return launch_split<KBITS, VBITS, 1>(D, grid, st, P);
-        case 2: return launch_split<KBITS, VBITS, 2>(D, grid, st, P);
-        case 4: return launch_split<KBITS, VBITS, 4>(D, grid, st, P);
-        case 8: return launch_split<KBITS, VBITS, 8>(D, grid, st, P);
+        case 1: return launch_split<KBITS, VBITS, 1>(D, grid, st, P, tma);
+        case 2: return launch_split<KBITS, VBITS, 2>(D, grid, st, P, tma);
+        case 4: return launch_split<KBITS, VBITS, 4>(D, grid, st, P, tma);
+        case 8: return launch_split<KBITS, VBITS, 8>(D, grid, st, P, tma);
     }
     return fail(KVQ_ERR_UNSUPPORTED, "decode_attn: Hq/H must be 1, 2, 4 or 8 (got %d)", G);
 }
 
-int choose_splits(int64_t B, int64_t H, int64_t T) {
-    const int64_t target = 4LL * sm_count();
+int choose_splits(int64_t B, int64_t H, int64_t T, int64_t G) {
+    // TMA variant (G <= 2): one wave of 256-thread CTAs at KVQ_ATTN_CTAS_PER_SM per SM; register-staged variant
+    // (G >= 4, 128-thread CTAs): four per SM
+    const int64_t target = (G <= 2 ? (int64_t)KVQ_ATTN_CTAS_PER_SM : 4) * sm_count();
     int64_t n = (target + B * H - 1) / (B * H);
     const int64_t max_n = (T + 255) / 256;
     if (n > max_n) n = max_n;
@@ -311,7 +607,7 @@ using namespace kvq;
 
 extern "C" int64_t kvq_decode_attn_workspace_bytes(int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, int* n_splits) {
     if (B <= 0 || Hq <= 0 || H <= 0 || T <= 0 || D <= 0) { if (n_splits) *n_splits = 1; return 0; }
-    const int n = choose_splits(B, H, T);
+    const int n = choose_splits(B, H, T, Hq / H);
     if (n_splits) *n_splits = n;
     return B * Hq * n * (D + 2) * (int64_t)sizeof(float);
 }
@@ -350,10 +646,15 @@ extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, 
     const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
     const int G = (int)(Hq / H);
     int rc;
-    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P);
-    else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P);
-    else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P);
-    else rc = launch_g<4, 8>(G, (int)D, grid, st, P);
+    // the bulk-copy pipeline needs each plane's rows back to back (true for the cache store) and 16-byte aligned
+    // scale vectors; KVQ_ATTN_NO_TMA=1 forces the register-staged variant (A/B measurements)
+    static const bool no_tma = getenv("KVQ_ATTN_NO_TMA") != nullptr;
+    const bool tma = !no_tma && ks.sT == kw && vs.sT == vw && (reinterpret_cast<uintptr_t>(k_scale) % 16) == 0 &&
+                     (reinterpret_cast<uintptr_t>(v_scale) % 16) == 0;
+    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
+    else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P, tma);
+    else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P, tma);
+    else rc = launch_g<4, 8>(G, (int)D, grid, st, P, tma);
     if (rc != KVQ_OK) return rc;
     rc = check_launch("decode_attn_split");
     if (rc != KVQ_OK) return rc;

@@ -38,6 +38,36 @@ def timeit(fn, iters=20, warm=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def timeit_graph(fn, n_variants, reps=10):
+    """GPU time per call with the CPU out of the way: capture `reps` rounds over all variants in one CUDA
+    graph (the C ABI launches on torch's current stream, so they are captured) and replay it."""
+    for i in range(n_variants):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            for i in range(n_variants):
+                fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / (reps * n_variants))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def report_graph(name, nbytes, fn, n_variants):
+    med, best = timeit_graph(fn, n_variants)
+    gbs = nbytes / med / 1e6
+    print(f"{name:44s} {med:8.4f} ms  {gbs:8.1f} GB/s  {100 * gbs / PEAK:5.1f}% of measured {PEAK:.0f}  {100 * gbs / 8000:5.1f}% of 8 TB/s  (best {nbytes / best / 1e6:.0f}) [graph]", flush=True)
+    return gbs
+
+
 def report(name, nbytes, fn, **kw):
     med, best = timeit(fn, **kw)
     gbs = nbytes / med / 1e6
@@ -100,7 +130,7 @@ def main():
         c2q = torch.empty(16, 12, 1024, 64, dtype=torch.int8, device=dev)
         sh2, sd2 = L.shape_stride(c2[0])
         n2 = c2[0].numel()
-        report("C2 per-token fused int8 fp16 [16,12,1024,64]", 3 * n2, lambda i: lib.kvq_quant_per_token_fused(c2[i % 24].data_ptr(), L.F16, sh2, sd2, 8, 1e-8, c2q.data_ptr(), None, scT.data_ptr(), s32.data_ptr(), bitsT.data_ptr(), st))
+        report_graph("C2 per-token fused int8 fp16 [16,12,1024,64]", 3 * n2, lambda i: lib.kvq_quant_per_token_fused(c2[i % 24].data_ptr(), L.F16, sh2, sd2, 8, 1e-8, c2q.data_ptr(), None, scT.data_ptr(), s32.data_ptr(), bitsT.data_ptr(), L.stream_ptr(dev)), 24)
         del outs, c2
     if "quant" in which or "token" in which:
         del xs
@@ -143,8 +173,8 @@ def main():
                 q = torch.randn(Ba, Ha * G, 1, Da, device=dev, dtype=torch.bfloat16)
                 nbytes = Ba * Ha * Ta * (Da * kb // 8 + Da * vb // 8) + 8 * Ta
                 ws = torch.empty(64 << 20, dtype=torch.float32, device=dev)
-                g = report(f"decode attn {mode} G={G} B8 H1 T65536 D128", nbytes,
-                           lambda i: kvq_b200.decode_attention_quantized(q, kcs[i % nl], ksc, kb, vcs[i % nl], vsc, vb, workspace=ws))
+                g = report_graph(f"decode attn {mode} G={G} B8 H1 T65536 D128", nbytes,
+                                 lambda i: kvq_b200.decode_attention_quantized(q, kcs[i % nl], ksc, kb, vcs[i % nl], vsc, vb, workspace=ws), nl)
                 del kcs, vcs
     print("launches", L.launch_count)
 
