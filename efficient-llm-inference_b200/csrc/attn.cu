@@ -536,22 +536,330 @@ __global__ void __launch_bounds__(kThreads2) decode_attn_tma_kernel(AttnParams P
     }
 }
 
+// =====================================================================================================
+// Integer-dot variant for G == 1 (MHA-shape decode: the bandwidth-bound case).  The fp32 variants spend
+// ~3 instructions per K element and ~3.4 per V element (PRMT + FADD to convert a code, FFMA to use it) and
+// are issue-bound at ~35 % of HBM.  Codes are already integers, so both contractions run on DP4A:
+//   scores : q is turned into 24-bit fixed point per head (three balanced signed byte planes, |error| <=
+//            2^-23 max|q|, i.e. fp32 precision); a lane's 16 codes cost 12 DP4A instead of 48 PRMT/FADD/FFMA.
+//   output : the weights p_t * v_scale[t] are turned into 24-bit fixed point against max(v_scale) (p <= 1);
+//            four tokens' code words are byte-transposed in registers (8 PRMT) so that one DP4A accumulates
+//            four tokens of one channel; int32 accumulators are flushed to fp32 only when the running max moves.
+// Same TMA ring, same split / merge protocol as the fp32 TMA variant.
+// =====================================================================================================
+
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) { return __dp4a((int)a, (int)b, c); }
+__device__ __forceinline__ int dp4a_us(uint32_t a_unsigned, uint32_t b_signed, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_unsigned), "r"(b_signed), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_su(uint32_t a_signed, uint32_t b_unsigned, int c) {
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed), "r"(b_unsigned), "r"(c));
+    return d;
+}
+// rows a,b,c,d of 4 bytes -> columns: col[j] = (a_j, b_j, c_j, d_j)
+__device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t col[4]) {
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
+    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
+    col[0] = __byte_perm(t0, t1, 0x5410); col[1] = __byte_perm(t0, t1, 0x7632);
+    col[2] = __byte_perm(t2, t3, 0x5410); col[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+constexpr float kFixedMax = 8355000.f;  // < 127 * (65536 + 256 + 1): three balanced byte digits cannot overflow
+
+template <int KBITS, int VBITS, int D>
+__global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams P) {
+    using C = TmaCfg<KBITS, VBITS, 1, D>;
+    constexpr int LPR = D / 16, KROWS = kThreads2 / LPR, KPASS = kTile / KROWS;
+    constexpr int WPR = D / 8;                   // V: lanes per row, each owns 8 consecutive channels
+    constexpr int VROWS = kThreads2 / WPR;       // 16 (D=128) / 32 (D=64)
+    constexpr int TPT = kTile / VROWS;           // tokens per thread per tile: 8 / 4
+    constexpr int NG = TPT / 4;                  // groups of four tokens
+    constexpr int VB = 8 * VBITS / 8;            // bytes a lane reads per row: 8 (INT8) / 4 (INT4)
+    constexpr int kWarps = kThreads2 / 32;
+    static_assert(TPT % 4 == 0, "token groups");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* p_s = reinterpret_cast<float*>(smem_raw + C::kBuf);          // [kTile] scores; q staging during setup
+    float* wmax_s = p_s + kTile;                                        // [8]
+    float* misc_s = wmax_s + 8;                                         // [8]: 0 = max|q|, 1 = max v_scale, 2.. scratch
+    uint8_t* wq_s = reinterpret_cast<uint8_t*>(misc_s + 8);             // [3][kTile] weight digits, thread order
+    int8_t* qd_s = reinterpret_cast<int8_t*>(wq_s + 3 * kTile);         // [3][D] q digits
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(qd_s + 3 * D) + 7) & ~uintptr_t(7));
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t_begin = split * P.tokens_per_split;
+    const int t_end = min(P.T, t_begin + P.tokens_per_split);
+    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
+    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto issue = [&](int tile_idx) {
+        const int s = tile_idx % C::kStages;
+        const int t0 = t_begin + tile_idx * kTile;
+        const int rows = min(kTile, t_end - t0);
+        uint8_t* sb = smem_raw + s * C::kStage;
+        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
+        mbar_expect_tx(&full[s], kb + vb);
+        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
+        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+    };
+    __syncthreads();  // barriers initialised before the first bulk copy can complete on them
+    if (tid == 0) {
+        for (int i = 0; i < C::kStages - 1 && i < n_tiles; ++i) issue(i);
+    }
+
+    // ---- setup: q -> 24-bit fixed point (three signed byte planes); max v_scale of the split
+    float qv = 0.f;
+    if (tid < D) qv = load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + h) * D + tid) * P.qk_scale_log2;
+    float vmax = 0.f;
+    for (int t = t_begin + tid; t < t_end; t += kThreads2 * 8) {  // 8 independent loads in flight
+        float v8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v8[u] = t + u * kThreads2 < t_end ? __ldg(P.v_scale + t + u * kThreads2) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) vmax = fmaxf(vmax, v8[u]);
+    }
+    float qa = fabsf(qv);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { qa = fmaxf(qa, __shfl_xor_sync(0xffffffffu, qa, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); }
+    if (lane == 0) { wmax_s[warp] = qa; p_s[warp] = vmax; }
+    __syncthreads();
+    float qmax = 0.f, vsmax = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < kWarps; ++w8) { qmax = fmaxf(qmax, wmax_s[w8]); vsmax = fmaxf(vsmax, p_s[w8]); }
+    const float dq = qmax > 0.f ? qmax / kFixedMax : 1.f;   // q = Q * dq
+    const float dw = vsmax > 0.f ? vsmax / kFixedMax : 1.f; // weight = W * dw
+    const float inv_dw = 1.f / dw;
+    if (tid < D) {
+        const int Q = __float2int_rn(qv / dq);
+        const int d0 = ((Q + 128) & 255) - 128, Q1 = (Q - d0) >> 8;
+        const int d1 = ((Q1 + 128) & 255) - 128, d2 = (Q1 - d1) >> 8;
+        qd_s[tid] = (int8_t)d0; qd_s[D + tid] = (int8_t)d1; qd_s[2 * D + tid] = (int8_t)d2;
+    }
+    __syncthreads();
+
+    const int kc = tid % LPR, kr = tid / LPR;
+    const int vc = tid % WPR, vr = tid / WPR;
+    // this lane's 16 channels of q, three planes x four words, in the element order of the K words
+    uint32_t qk[3][4];
+    int kinit[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const uint4 t = *reinterpret_cast<const uint4*>(qd_s + pl * D + kc * 16);
+        if (KBITS == 8) { qk[pl][0] = t.x; qk[pl][1] = t.y; qk[pl][2] = t.z; qk[pl][3] = t.w; kinit[pl] = 0; }
+        else {
+            // INT4 rows: word j holds elements 8j..8j+7, high nibbles = even elements, low = odd
+            qk[pl][0] = __byte_perm(t.x, t.y, 0x6420); qk[pl][1] = __byte_perm(t.x, t.y, 0x7531);
+            qk[pl][2] = __byte_perm(t.z, t.w, 0x6420); qk[pl][3] = __byte_perm(t.z, t.w, 0x7531);
+            // nibbles are used unsigned (code + 8): start the accumulator at -8 * sum(q digits)
+            kinit[pl] = -8 * (dp4a_ss(0x01010101u, t.x, 0) + dp4a_ss(0x01010101u, t.y, 0) + dp4a_ss(0x01010101u, t.z, 0) +
+                              dp4a_ss(0x01010101u, t.w, 0));
+        }
+    }
+
+    float ksn[KPASS], vsn = 0.f;  // scales one tile ahead: K rows of this lane; V scale of token `tid` of the tile
+    auto fetch_scales = [&](int tile_idx) {
+        const int t0 = t_begin + tile_idx * kTile;
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) { const int t = t0 + ps * KROWS + kr; ksn[ps] = t < t_end ? __ldg(P.k_scale + t) : 0.f; }
+        if (tid < kTile) vsn = t0 + tid < t_end ? __ldg(P.v_scale + t0 + tid) : 0.f;
+    };
+    fetch_scales(0);
+
+    int iacc[8][3];
+    float facc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { facc[d] = 0.f; iacc[d][0] = iacc[d][1] = iacc[d][2] = 0; }
+    float m_run = -INFINITY, l_loc = 0.f;
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % C::kStages;
+        if (tid == 0 && it + C::kStages - 1 < n_tiles) issue(it + C::kStages - 1);
+        float ksc[KPASS];
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) ksc[ps] = ksn[ps];
+        const float vs_tok = vsn;
+        if (it + 1 < n_tiles) fetch_scales(it + 1);
+        while (!mbar_try_wait(&full[s], (it / C::kStages) & 1)) {}
+        const uint8_t* sb = smem_raw + s * C::kStage;
+        const int rows = min(kTile, t_end - (t_begin + it * kTile));
+
+        // ---- K phase
+        float wm = -INFINITY;
+#pragma unroll
+        for (int ps = 0; ps < KPASS; ++ps) {
+            const int row = ps * KROWS + kr;
+            int a0 = kinit[0], a1 = kinit[1], a2 = kinit[2];
+            if (KBITS == 8) {
+                const uint4 kw = *reinterpret_cast<const uint4*>(sb + row * C::kKRow + kc * 16);
+                const uint32_t w[4] = {kw.x, kw.y, kw.z, kw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a0 = dp4a_ss(w[j], qk[0][j], a0); a1 = dp4a_ss(w[j], qk[1][j], a1); a2 = dp4a_ss(w[j], qk[2][j], a2); }
+            } else {
+                const uint2 kw = *reinterpret_cast<const uint2*>(sb + row * C::kKRow + kc * 8);
+                const uint32_t w[4] = {(kw.x >> 4) & 0x0f0f0f0fu, kw.x & 0x0f0f0f0fu, (kw.y >> 4) & 0x0f0f0f0fu, kw.y & 0x0f0f0f0fu};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a0 = dp4a_us(w[j], qk[0][j], a0); a1 = dp4a_us(w[j], qk[1][j], a1); a2 = dp4a_us(w[j], qk[2][j], a2); }
+            }
+            float d = fmaf((float)a2, 65536.f, fmaf((float)a1, 256.f, (float)a0));
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            const float sv = row < rows ? d * (dq * ksc[ps]) : -INFINITY;
+            if (kc == 0) p_s[row] = sv;
+            wm = fmaxf(wm, sv);
+        }
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        if (lane == 0) wmax_s[warp] = wm;
+        __syncthreads();
+
+        // ---- weights: running max, p = exp2(s - m), fixed-point weight digits in thread order
+        float mt = -INFINITY;
+#pragma unroll
+        for (int w8 = 0; w8 < kWarps; ++w8) mt = fmaxf(mt, wmax_s[w8]);
+        const float m_new = fmaxf(m_run, mt);
+        if (m_new != m_run) {  // uniform: flush the integer accumulators into fp32 and rescale
+            const float a = m_run == -INFINITY ? 0.f : exp2f(m_run - m_new);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const float v = fmaf((float)iacc[d][2], 65536.f, fmaf((float)iacc[d][1], 256.f, (float)iacc[d][0]));
+                facc[d] = fmaf(v, dw, facc[d]) * a;
+                iacc[d][0] = iacc[d][1] = iacc[d][2] = 0;
+            }
+            l_loc *= a;
+            m_run = m_new;
+        }
+        if (tid < kTile) {
+            const float sv = p_s[tid];
+            const float pw = sv == -INFINITY ? 0.f : exp2f(sv - m_new);
+            l_loc += pw;
+            const uint32_t W = (uint32_t)__float2int_rn(pw * vs_tok * inv_dw);
+            const int slot = (tid % VROWS) * TPT + tid / VROWS;  // the TPT tokens of row group vr are contiguous
+            wq_s[slot] = (uint8_t)(W & 255u); wq_s[kTile + slot] = (uint8_t)((W >> 8) & 255u); wq_s[2 * kTile + slot] = (uint8_t)(W >> 16);
+        }
+        __syncthreads();
+
+        // ---- V phase: byte-transpose four tokens' words, one DP4A per (channel, weight plane)
+        uint32_t wd[3][NG];
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+            for (int j = 0; j < NG; ++j) wd[pl][j] = *reinterpret_cast<const uint32_t*>(wq_s + pl * kTile + vr * TPT + 4 * j);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            uint32_t lo[4], hi[4];  // INT8: lo = channels 0..3, hi = channels 4..7 (signed bytes); INT4: odd / even channels
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint8_t* src = sb + C::kKTile + (vr + VROWS * (4 * j + i)) * C::kVRow + vc * VB;
+                if (VBITS == 8) { const uint2 t = *reinterpret_cast<const uint2*>(src); lo[i] = t.x; hi[i] = t.y; }
+                else {
+                    const uint32_t t = *reinterpret_cast<const uint32_t*>(src);
+                    lo[i] = __vsub4(t & 0x0f0f0f0fu, 0x08080808u);          // elements 1,3,5,7
+                    hi[i] = __vsub4((t >> 4) & 0x0f0f0f0fu, 0x08080808u);   // elements 0,2,4,6
+                }
+            }
+            uint32_t cl[4], ch[4];
+            transpose4x4(lo[0], lo[1], lo[2], lo[3], cl);
+            transpose4x4(hi[0], hi[1], hi[2], hi[3], ch);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                // channel index inside the lane's 8: INT8 -> lo: c4, hi: 4 + c4; INT4 -> lo: 2*c4 + 1, hi: 2*c4
+                const int dl = VBITS == 8 ? c4 : 2 * c4 + 1, dh = VBITS == 8 ? 4 + c4 : 2 * c4;
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    iacc[dl][pl] = dp4a_su(cl[c4], wd[pl][j], iacc[dl][pl]);
+                    iacc[dh][pl] = dp4a_su(ch[c4], wd[pl][j], iacc[dh][pl]);
+                }
+            }
+        }
+        __syncthreads();  // releases stage s, p_s, wq_s, wmax_s
+    }
+
+    // ---- final flush, reduce the VROWS row groups and the per-thread sums
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const float v = fmaf((float)iacc[d][2], 65536.f, fmaf((float)iacc[d][1], 256.f, (float)iacc[d][0]));
+        facc[d] = fmaf(v, dw, facc[d]);
+    }
+    float* red_s = reinterpret_cast<float*>(smem_raw);  // [VROWS][D], then [kThreads2] for l
+#pragma unroll
+    for (int d = 0; d < 8; ++d) red_s[vr * D + vc * 8 + d] = facc[d];
+    float* lred = red_s + VROWS * D;
+    lred[tid] = tid < kTile ? l_loc : 0.f;
+    __syncthreads();
+    const int64_t hq = (int64_t)b * P.Hq + h;
+    if (tid < D) {
+        float sum = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < VROWS; ++r) sum += red_s[r * D + tid];
+        P.ws_acc[(hq * P.n_splits + split) * D + tid] = sum;
+    }
+    if (warp == kWarps - 1) {
+        float ls = 0.f;
+        for (int i = lane; i < kTile; i += 32) ls += lred[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        if (lane == 0) {
+            P.ws_ml[(hq * P.n_splits + split) * 2] = m_run;
+            P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = ls;
+        }
+    }
+}
+
 template <int ODT>
 __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
                                          void* __restrict__ out) {
+    // launched with programmatic stream serialization: everything above this line overlaps the split kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t hq = blockIdx.x;
     const int d = threadIdx.x;
     if (d >= D) return;
-    float M = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws_ml[(hq * n_splits + s) * 2]);
-    float num = 0.f, den = 0.f;
-    for (int s = 0; s < n_splits; ++s) {
-        const float m = ws_ml[(hq * n_splits + s) * 2];
-        const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-        num = fmaf(ws_acc[(hq * n_splits + s) * D + d], w, num);
-        den = fmaf(ws_ml[(hq * n_splits + s) * 2 + 1], w, den);
+    const float2* ml = reinterpret_cast<const float2*>(ws_ml) + hq * n_splits;
+    const float* acc = ws_acc + hq * n_splits * D + d;
+    float M = -INFINITY, num = 0.f, den = 0.f;
+    for (int s0 = 0; s0 < n_splits; s0 += 8) {  // 8 splits per round: independent loads, then an online-softmax merge
+        float2 m8[8];
+        float a8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = s0 + u < n_splits;
+            m8[u] = ok ? ml[s0 + u] : make_float2(-INFINITY, 0.f);
+            a8[u] = ok ? acc[(int64_t)(s0 + u) * D] : 0.f;
+        }
+        float Mn = M;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) Mn = fmaxf(Mn, m8[u].x);
+        const float r = M == -INFINITY ? 0.f : exp2f(M - Mn);
+        num *= r; den *= r; M = Mn;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float w = m8[u].x == -INFINITY ? 0.f : exp2f(m8[u].x - M);
+            num = fmaf(a8[u], w, num);
+            den = fmaf(m8[u].y, w, den);
+        }
     }
     store_scalar<ODT>(out, hq * D + d, num / den);
+}
+
+template <int ODT>
+int launch_merge(unsigned blocks, unsigned threads, cudaStream_t st, const float* ws_acc, const float* ws_ml, int n_splits, int D, void* out) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    KVQ_CUDA(cudaLaunchKernelEx(&cfg, decode_attn_merge_kernel<ODT>, ws_acc, ws_ml, n_splits, D, out));
+    return KVQ_OK;
 }
 
 template <int KBITS, int VBITS, int G, int D>
@@ -569,8 +877,28 @@ int launch_tma(dim3 grid, cudaStream_t st, const AttnParams& P) {
     return KVQ_OK;
 }
 
+template <int KBITS, int VBITS, int D>
+int launch_dp4a(dim3 grid, cudaStream_t st, const AttnParams& P) {
+    using C = TmaCfg<KBITS, VBITS, 1, D>;
+    constexpr int kSmem = C::kBuf + (kTile + 16) * 4 + 3 * kTile + 3 * D + C::kStages * 8 + 32;
+    auto kern = decode_attn_dp4a_kernel<KBITS, VBITS, D>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    KVQ_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        configured_dev = dev;
+    }
+    kern<<<grid, kThreads2, kSmem, st>>>(P);
+    return KVQ_OK;
+}
+
 template <int KBITS, int VBITS, int G>
 int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
+    if constexpr (G == 1) {  // MHA-shape decode: integer-dot variant (KVQ_ATTN_FP32=1 keeps the fp32 TMA variant for A/B runs)
+        static const bool fp32_only = getenv("KVQ_ATTN_FP32") != nullptr;
+        if (tma && !fp32_only) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
+    }
     if constexpr (G <= 2) {  // GQA groups of 4 / 8 are FMA-bound: the register-staged variant is faster there
         if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
     }
@@ -660,9 +988,10 @@ extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, 
     if (rc != KVQ_OK) return rc;
     const unsigned mt = (unsigned)D;
     switch (out_dtype) {
-        case KVQ_F32: decode_attn_merge_kernel<KVQ_F32><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
-        case KVQ_F16: decode_attn_merge_kernel<KVQ_F16><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
-        default: decode_attn_merge_kernel<KVQ_BF16><<<(unsigned)(B * Hq), mt, 0, st>>>(P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        case KVQ_F16: rc = launch_merge<KVQ_F16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        default: rc = launch_merge<KVQ_BF16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
     }
+    if (rc != KVQ_OK) return rc;
     return check_launch("decode_attn_merge");
 }
