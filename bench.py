@@ -174,7 +174,7 @@ def workload_config(cfg, n_gpus, where):
         "workload": (f"Llama-3-8B-shape synthetic KV (L={cfg['L']} x {{K,V}}, B={cfg['B']}, H={cfg['H']} KV heads, T={cfg['T']}, "
                      f"D={cfg['D']}, bf16): INT4 pack/unpack, per-tensor scale, head-sharded over {n_gpus} GPU(s)"),
         "baseline_config": "BASELINE.json configs[2]",
-        "step": "per layer tensor: absmax -> [allreduce-max] -> quantize+pack -> unpack+dequantize",
+        "step": "absmax of all 64 layer tensors (1 launch) -> [allreduce-max] -> quantize+pack (1 launch) -> unpack+dequantize (1 launch)",
         "algorithmic_bytes_per_element": 7.0,
         "l2_policy": "inputs (64 GiB whole job) are far larger than the 126 MB L2; no flush needed",
         "parallelism": f"kv-head shard x{n_gpus}" if where == "gpu" else "cpu",
@@ -222,32 +222,30 @@ def run_c3(args, cfg):
                 x[:, h - lo] = torch.randn(B, T, D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             xs.append(x)
     packed = [torch.empty(B, Hl, T, D // 2, device=dev, dtype=torch.uint8) for _ in range(n_tensors)]
-    outs = [torch.empty(B, Hl, T, D, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+    outs = [torch.empty(B, Hl, T, D, device=dev, dtype=torch.bfloat16) for _ in range(n_tensors)]
     bits = torch.zeros(n_tensors, dtype=torch.int32, device=dev)
     scales = torch.empty(n_tensors, dtype=torch.bfloat16, device=dev)
-    shs = [L.shape_stride(x) for x in xs]
+    from kvq_b200.quantization import TensorTable
+    tx, tp, to = TensorTable(xs), TensorTable(packed), TensorTable(outs)
     stream = L.stream_ptr(dev)
     dom_events = []  # (start, end) around every launch of the dominant kernel inside the timed region
 
     def step(timed: bool):
-        for i, x in enumerate(xs):  # phase 1 for the whole batch
-            sh, st = shs[i]
-            L.check(lib.kvq_absmax(x.data_ptr(), L.BF16, sh, st, L.PER_TENSOR, bits[i:].data_ptr(), 0, stream), "kvq_absmax")
+        # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between
+        L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
         if world > 1:
             dist.all_reduce(bits, op=dist.ReduceOp.MAX)  # the only collective on the path
-        for i, x in enumerate(xs):  # phase 2 + unpack
-            sh, st = shs[i]
-            L.check(lib.kvq_quant_int4_pack(x.data_ptr(), L.BF16, sh, st, L.PER_TENSOR, bits[i:].data_ptr(), 1e-8, packed[i].data_ptr(),
-                                            None, scales[i:].data_ptr(), None, stream), "kvq_quant_int4_pack")
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            L.check(lib.kvq_dequant_int4_unpack(packed[i].data_ptr(), sh, None, scales[i:].data_ptr(), L.BF16, L.PER_TENSOR,
-                                                outs[i % 4].data_ptr(), L.BF16, stream), "kvq_dequant_int4_unpack")
-            if timed:
-                e1.record()
-                dom_events.append((e0, e1))
-        return 3 * n_tensors
+        L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
+                                      scales.data_ptr(), None, stream), "kvq_quant_batched")
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(lib.kvq_dequant_batched(tp.ptrs.data_ptr(), 4, n_tensors, n_local, scales.data_ptr(), L.BF16, to.ptrs.data_ptr(),
+                                        L.BF16, stream), "kvq_dequant_batched")
+        if timed:
+            e1.record()
+            dom_events.append((e0, e1))
+        return 3
 
     def sync_all():
         if world > 1:
@@ -279,7 +277,7 @@ def run_c3(args, cfg):
     # roofline of the dominant kernel (dequant_flat_kernel<bf16, INT4>): algorithmic N*(0.5+2) bytes per launch
     dom_ms = statistics.mean(a.elapsed_time(b) for a, b in dom_events)
     peak, peak_src = measured_peak()
-    dom_bytes = 2.5 * n_local
+    dom_bytes = 2.5 * n_local * n_tensors  # one launch covers all layer tensors
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
 
     # parity spot check inside the run: codes of tensor 0 against the exact formula on a sample
@@ -291,7 +289,7 @@ def run_c3(args, cfg):
     got = torch.where(idx % 2 == 0, byte >> 4, byte & 15) - 8
     assert torch.equal(got, want), "bench parity spot check failed"
 
-    del xs, packed, outs, x0, x  # the e2e leg brings its data from the host
+    del xs, packed, outs, x0, x, tx, tp, to  # the e2e leg brings its data from the host
     torch.cuda.empty_cache()
     e2e = run_e2e(args, cfg, dev, Hl, world) if not args.skip_e2e else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
                                                                           "d2h_bytes_per_step": 0, "_ms": 1.0, "_job_bytes": 0.0}
@@ -318,7 +316,7 @@ def run_c3(args, cfg):
             "roofline": {"bound": "hbm", "kernel": "dequant_flat_kernel<bf16,int4> (unpack+dequantize)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms, "launches_timed": len(dom_events),
-                         "traffic": ncu_traffic("dequant_flat_int4_bf16")},
+                         "traffic": (lambda t: None if t is None else t * n_tensors * n_local / (16 * 8 * 32768 * 128))(ncu_traffic("dequant_flat_int4_bf16"))},
             "cpu_baseline": cpu,
             "sm_count": sm.value,
         }

@@ -117,49 +117,63 @@ template <int DT, int BITS> struct OutBytes { static constexpr int value = InVec
 
 // ---- flat kernels: contiguous input and output, per-tensor scale ---------------------------------------------
 
+// Batched form (xs != nullptr): n_tensors tensors of n_vec vectors each, walked IN ORDER by every CTA (grid-stride inside
+// each tensor), so the whole grid streams through one tensor at a time exactly like n separate launches would, without the
+// launch gaps.  Entry i of absmax_bits / scale_out / scale_f32_out belongs to tensor i.
 template <int DT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
-                                                               uint32_t* __restrict__ absmax_bits) {
+                                                               uint32_t* __restrict__ absmax_bits,
+                                                               const void* const* __restrict__ xs = nullptr, int n_tensors = 1) {
     __shared__ uint32_t red[kThreads / 32];
-    uint32_t m = 0;
     const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-        uint4 v[UNROLL];
+    for (int ti = 0; ti < n_tensors; ++ti) {
+        const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
+        uint32_t m = 0;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+            uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t j = i + (int64_t)u * kThreads;
-            v[u] = j < n_vec ? ld_stream(x + j) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t j = i + (int64_t)u * kThreads;
+                v[u] = j < n_vec ? ld_stream(xt + j) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
         }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
+        m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+        if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits + ti, m);
+        __syncthreads();  // `red` is reused by the next tensor
     }
-    m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
-    if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits, m);
 }
 
 template <int DT, int BITS, int UNROLL>
 __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
                                                               const uint32_t* __restrict__ absmax_bits, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
-                                                              float* __restrict__ scale_f32_out) {
+                                                              float* __restrict__ scale_f32_out,
+                                                              const void* const* __restrict__ xs = nullptr,
+                                                              void* const* __restrict__ qs = nullptr, int n_tensors = 1) {
     constexpr int kOut = OutBytes<DT, BITS>::value;
-    const Scale sc = scale_from_bits<BITS>(absmax_bits[0], eps);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (scale_out) store_scalar<DT>(scale_out, 0, sc.s);
-        if (scale_f32_out) scale_f32_out[0] = round_through<DT>(sc.s);
-    }
     const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-        uint4 v[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) v[u] = ld_stream(x + j);
+    for (int ti = 0; ti < n_tensors; ++ti) {
+        const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
+        char* qt = xs ? reinterpret_cast<char*>(qs[ti]) : q;
+        const Scale sc = scale_from_bits<BITS>(absmax_bits[ti], eps);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (scale_out) store_scalar<DT>(scale_out, ti, sc.s);
+            if (scale_f32_out) scale_f32_out[ti] = round_through<DT>(sc.s);
         }
+        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+            uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) quant_store<DT, BITS>(v[u], sc, q + j * kOut);
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t j = i + (int64_t)u * kThreads;
+                if (j < n_vec) v[u] = ld_stream(xt + j);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t j = i + (int64_t)u * kThreads;
+                if (j < n_vec) quant_store<DT, BITS>(v[u], sc, qt + j * kOut);
+            }
         }
     }
 }
@@ -519,22 +533,28 @@ __device__ __forceinline__ void dequant_store(const Raw<CodeIn<ODT, BITS>::kByte
 template <int ODT, int BITS, bool PK, int UNROLL>
 __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __restrict__ codes, int64_t n_vec,
                                                                 const void* __restrict__ scale, int scale_dtype,
-                                                                uint4* __restrict__ out) {
+                                                                uint4* __restrict__ out,
+                                                                const void* const* __restrict__ cs = nullptr,
+                                                                void* const* __restrict__ os = nullptr, int n_tensors = 1) {
     constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
-    ScaleArg<PK> sa;
-    sa.load(scale, scale_dtype, 0);
     const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-        Raw<kIn> r[UNROLL];
+    for (int ti = 0; ti < n_tensors; ++ti) {  // batched form: tensors in order, one scale each (see absmax_flat_kernel)
+        const char* ct = cs ? reinterpret_cast<const char*>(cs[ti]) : codes;
+        uint4* ot = cs ? reinterpret_cast<uint4*>(os[ti]) : out;
+        ScaleArg<PK> sa;
+        sa.load(scale, scale_dtype, ti);
+        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+            Raw<kIn> r[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) r[u].load(codes + j * kIn);
-        }
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t j = i + (int64_t)u * kThreads;
+                if (j < n_vec) r[u].load(ct + j * kIn);
+            }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sa, out + j);
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t j = i + (int64_t)u * kThreads;
+                if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sa, ot + j);
+            }
         }
     }
 }
@@ -874,4 +894,78 @@ extern "C" int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shap
                                        const void* scale, int scale_dtype, int granularity, void* out, int out_dtype,
                                        kvq_stream_t stream) {
     return dequant<4>(packed, shape, q_stride3, scale, scale_dtype, granularity, out, out_dtype, (cudaStream_t)stream);
+}
+
+// ---- batched (multi-tensor) forms: n contiguous tensors of `numel` elements each in ONE launch per phase ------------------
+// One launch per phase for a whole step (all layers x {K,V}) instead of one per tensor: at 1/8 of a cache per GPU the
+// per-tensor kernels last 20-30 us and launch gaps dominate.  Pointer tables live on the device.
+
+namespace kvq { namespace {
+unsigned batched_grid(int64_t n_vec, int unroll, int64_t) { return flat_grid(n_vec, unroll); }
+} }
+
+extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
+                                  kvq_stream_t stream) {
+    KVQ_REQUIRE(xs && absmax_bits, "null pointer");
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tensors == 0) return KVQ_OK;
+    KVQ_CUDA(cudaMemsetAsync(absmax_bits, 0, n_tensors * 4, st));
+    if (numel == 0) return KVQ_OK;
+    const int es = elem_size(dtype);
+    KVQ_REQUIRE((numel * es) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
+    const int64_t n_vec = numel * es / 16;
+    constexpr int U = 8;
+    KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(nullptr, n_vec, absmax_bits, xs, (int)n_tensors));
+    return check_launch("absmax_batched");
+}
+
+extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                                 const uint32_t* absmax_bits, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                                 kvq_stream_t stream) {
+    KVQ_REQUIRE(xs && qs && absmax_bits, "null pointer");
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
+    KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4");
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tensors == 0 || numel == 0) return KVQ_OK;
+    const int es = elem_size(dtype);
+    KVQ_REQUIRE((numel * es) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
+    const int64_t n_vec = numel * es / 16;
+    constexpr int U = 4;
+    if (bits == 8) {
+        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, 8, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(
+                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors));
+    } else {
+        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, 4, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(
+                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors));
+    }
+    return check_launch("quant_batched");
+}
+
+extern "C" int kvq_dequant_batched(const void* const* codes, int bits, int64_t n_tensors, int64_t numel, const void* scales,
+                                   int scale_dtype, void* const* outs, int out_dtype, kvq_stream_t stream) {
+    KVQ_REQUIRE(codes && outs && scales, "null pointer");
+    KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4");
+    KVQ_REQUIRE(scale_dtype >= 0 && scale_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tensors == 0 || numel == 0) return KVQ_OK;
+    const int oes = elem_size(out_dtype);
+    KVQ_REQUIRE((numel * oes) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
+    const int64_t n_vec = numel * oes / 16;
+    const bool pk = scale_dtype == out_dtype && out_dtype != KVQ_F32;
+    constexpr int U = 4;
+    const unsigned grid = batched_grid(n_vec, U, n_tensors);
+#define KVQ_DQB(ODT, BITS, PK) dequant_flat_kernel<ODT, BITS, PK, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, scales, scale_dtype, nullptr, codes, outs, (int)n_tensors)
+    if (bits == 8) {
+        if (pk) { if (out_dtype == KVQ_F16) KVQ_DQB(KVQ_F16, 8, true); else KVQ_DQB(KVQ_BF16, 8, true); }
+        else { KVQ_DISPATCH_DT(out_dtype, KVQ_DQB(DT, 8, false)); }
+    } else {
+        if (pk) { if (out_dtype == KVQ_F16) KVQ_DQB(KVQ_F16, 4, true); else KVQ_DQB(KVQ_BF16, 4, true); }
+        else { KVQ_DISPATCH_DT(out_dtype, KVQ_DQB(DT, 4, false)); }
+    }
+#undef KVQ_DQB
+    return check_launch("dequant_batched");
 }

@@ -52,6 +52,9 @@ SIGNATURES = {
     "kvq_quant_per_token_fused": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "kvq_dequant_int8": (c_int, [c_vp, I64x4, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "kvq_dequant_int4_unpack": (c_int, [c_vp, I64x4, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
+    "kvq_absmax_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
+    "kvq_quant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp]),
+    "kvq_dequant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
     "kvq_evict_plan_make": (c_int, [c_int] + [c_i64] * 7 + [ctypes.POINTER(EvictPlan)]),
     "kvq_evict_indices_host": (c_int, [ctypes.POINTER(EvictPlan), c_vp]),
     "kvq_evict_indices_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),

@@ -3,6 +3,9 @@
 from .ops import (
     QuantizedKVCache,
     QuantizedLayerKV,
+    TensorTable,
+    dequantize_per_tensor_batched,
+    quantize_per_tensor_batched,
     dequantize_int4_per_tensor_packed,
     dequantize_int8_per_tensor,
     quantize_int4_per_tensor_packed,
@@ -16,4 +19,7 @@ __all__ = [
     "dequantize_int4_per_tensor_packed",
     "QuantizedLayerKV",
     "QuantizedKVCache",
+    "TensorTable",
+    "quantize_per_tensor_batched",
+    "dequantize_per_tensor_batched",
 ]

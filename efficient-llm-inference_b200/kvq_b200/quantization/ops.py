@@ -149,6 +149,65 @@ def dequantize_int4_per_tensor_packed(packed: torch.Tensor, scale: torch.Tensor,
     return out
 
 
+class TensorTable:
+    """Device-resident table of the data pointers of n same-shape contiguous CUDA tensors, for the batched
+    (one launch per phase for a whole step) entry points.  Build it once and reuse it: creating it copies n
+    pointers to the device."""
+
+    def __init__(self, tensors):
+        tensors = list(tensors)
+        if not tensors:
+            raise ValueError("empty tensor list")
+        L.require_cuda(*tensors)
+        t0 = tensors[0]
+        for t in tensors:
+            if t.shape != t0.shape or t.dtype != t0.dtype or t.device != t0.device or not t.is_contiguous():
+                raise RuntimeError("batched entry points need same-shape, same-dtype, contiguous tensors on one device")
+        self.tensors = tensors
+        self.shape, self.dtype, self.device, self.numel = t0.shape, t0.dtype, t0.device, t0.numel()
+        self.ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(t0.device, non_blocking=True)
+
+    def __len__(self):
+        return len(self.tensors)
+
+
+@torch.no_grad()
+def quantize_per_tensor_batched(xs: "TensorTable", codes: "TensorTable", bits: int, scales: torch.Tensor,
+                                eps: float = 1e-8, group=None, absmax_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """quantize_int8_per_tensor / quantize_int4_per_tensor_packed applied to every tensor of `xs` (each with its own
+    per-tensor scale) in TWO launches total (+ one allreduce when head-sharded).  Codes go to the preallocated tensors
+    of `codes`, scale.to(x.dtype) of tensor i to scales[i].  Returns the absmax bit patterns."""
+    n = len(xs)
+    if len(codes) != n or scales.numel() < n or scales.dtype != xs.dtype:
+        raise RuntimeError("codes / scales do not match the input table")
+    if bits == 4 and xs.shape[-1] % 2:
+        raise RuntimeError("batched INT4 needs an even last dimension")
+    if absmax_bits is None:
+        absmax_bits = torch.empty(n, dtype=torch.int32, device=xs.device)
+    with torch.cuda.device(xs.device):
+        st = L.stream_ptr(xs.device)
+        L.check(L.lib().kvq_absmax_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, absmax_bits.data_ptr(), st),
+                "kvq_absmax_batched")
+        allreduce_absmax_(absmax_bits, group)
+        L.check(L.lib().kvq_quant_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, int(bits), absmax_bits.data_ptr(),
+                                          float(eps), codes.ptrs.data_ptr(), scales.data_ptr(), None, st), "kvq_quant_batched")
+        L.count_launch(2)
+    return absmax_bits
+
+
+@torch.no_grad()
+def dequantize_per_tensor_batched(codes: "TensorTable", bits: int, scales: torch.Tensor, outs: "TensorTable") -> None:
+    """dequantize_int8_per_tensor / dequantize_int4_per_tensor_packed for every tensor of `codes` in ONE launch."""
+    n = len(codes)
+    if len(outs) != n or scales.numel() < n:
+        raise RuntimeError("outs / scales do not match the code table")
+    with torch.cuda.device(codes.device):
+        L.check(L.lib().kvq_dequant_batched(codes.ptrs.data_ptr(), int(bits), n, outs.numel, scales.data_ptr(),
+                                            L.dtype_code(scales.dtype), outs.ptrs.data_ptr(), L.dtype_code(outs.dtype),
+                                            L.stream_ptr(codes.device)), "kvq_dequant_batched")
+        L.count_launch(1)
+
+
 class _TokenStore:
     """Codes of one K or V stream: [B,H,cap,W] (W = D for INT8, ceil(D/2) for INT4) plus one scale per
     token in the input dtype (what the reference returns) and the same value widened to fp32 (what the

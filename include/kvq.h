@@ -133,6 +133,19 @@ KVQ_API int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shape[4
                             const void* scale, int scale_dtype, int granularity, void* out, int out_dtype,
                             kvq_stream_t stream);
 
+/* ---------------------------------------------------------------------------------- area 1: batched forms
+ * n contiguous tensors of `numel` elements each (all layers x {K, V} of a step) in ONE launch per phase, per-tensor
+ * granularity.  xs / qs / codes / outs are DEVICE arrays of n device pointers; absmax_bits, scale_out, scale_f32_out and
+ * scales hold one entry per tensor.  Same arithmetic as the single-tensor entry points (which they replace when the
+ * reference loops `for layer ... quantize(k); quantize(v)`, ops.py:323-342 / benchmarker.py:461,486). */
+KVQ_API int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
+                               kvq_stream_t stream);
+KVQ_API int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                              const uint32_t* absmax_bits, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                              kvq_stream_t stream);
+KVQ_API int kvq_dequant_batched(const void* const* codes, int bits, int64_t n_tensors, int64_t numel, const void* scales,
+                                int scale_dtype, void* const* outs, int out_dtype, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: eviction
  * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
  * of every destination row in registers; no index tensor and no intermediate parts list exists. */

@@ -123,6 +123,32 @@ def test_dequant_packed_path_corner_cases(kvq, oracle, dtype):
                 assert bits_equal(got.cpu(), oracle.dequantize_int4_per_tensor_packed(nib, s, 32, odt)), (sval, sdt, odt)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_batched_multi_tensor_matches_single(kvq, oracle, dtype, bits):
+    """One launch per phase over all tensors of a step == the per-tensor helpers applied one by one (bit-exact)."""
+    from kvq_b200.quantization import TensorTable, dequantize_per_tensor_batched, quantize_per_tensor_batched
+    xs = [gen((2, 4, 37, 64), dtype, 50 + i, outlier=(i % 2 == 0)) * (0.1 + i) for i in range(5)]
+    xs[3] = torch.zeros_like(xs[3])  # eps path inside a batch
+    xd = [x.to(dtype).cuda() for x in xs]
+    W = 64 if bits == 8 else 32
+    codes = [torch.empty((2, 4, 37, W), dtype=torch.int8 if bits == 8 else torch.uint8, device="cuda") for _ in xs]
+    outs = [torch.empty((2, 4, 37, 64), dtype=dtype, device="cuda") for _ in xs]
+    scales = torch.empty(len(xs), dtype=dtype, device="cuda")
+    tx, tc, to = TensorTable(xd), TensorTable(codes), TensorTable(outs)
+    quantize_per_tensor_batched(tx, tc, bits, scales)
+    dequantize_per_tensor_batched(tc, bits, scales, to)
+    for i, x in enumerate(xs):
+        x = x.to(dtype)
+        if bits == 8:
+            oq, os_ = oracle.quantize_int8_per_tensor(x)
+            want = oracle.dequantize_int8_per_tensor(oq, os_, dtype)
+        else:
+            oq, os_, last = oracle.quantize_int4_per_tensor_packed(x)
+            want = oracle.dequantize_int4_per_tensor_packed(oq, os_, last, dtype)
+        assert torch.equal(codes[i].cpu(), oq) and bits_equal(scales[i].cpu(), os_) and bits_equal(outs[i].cpu(), want), i
+
+
 def test_kvq_ext_facade(kvq, oracle):
     ext = kvq.get_cuda_extension()
     q = torch.randint(-127, 128, (3, 5, 16), dtype=torch.int8)
