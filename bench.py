@@ -37,6 +37,13 @@ for _p in (ROOT, os.path.join(ROOT, "efficient-llm-inference_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+_JSON_FD = 1
+
+
+def emit(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "kv_quant_dequant_hbm_gbs"
 UNIT = "GB/s"
 C3 = dict(L=32, B=16, H=8, T=32768, D=128)
@@ -166,7 +173,7 @@ def run_reference(args, cfg):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(cfg, n_gpus, where):
@@ -233,7 +240,7 @@ def run_c3(args, cfg):
     def step(timed: bool):
         # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between
         L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
-        if world > 1:
+        if world > 1 and not os.environ.get("KVQ_BENCH_NO_ALLREDUCE"):  # (env: debugging aid, not a valid bench line)
             dist.all_reduce(bits, op=dist.ReduceOp.MAX)  # the only collective on the path
         L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
                                       scales.data_ptr(), None, stream), "kvq_quant_batched")
@@ -320,7 +327,7 @@ def run_c3(args, cfg):
             "cpu_baseline": cpu,
             "sm_count": sm.value,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -410,6 +417,11 @@ def run_e2e(args, cfg, dev, Hl, world):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): libraries that print to fd 1 (NCCL's version banner does) go to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -117,6 +117,16 @@ template <int DT, int BITS> struct OutBytes { static constexpr int value = InVec
 
 // ---- flat kernels: contiguous input and output, per-tensor scale ---------------------------------------------
 
+// Chunk c of tensor ti (a chunk = kThreads * unroll vectors) belongs to CTA (ti * chunks_per_tensor + c) % gridDim.x: the
+// left-over chunks of every tensor start where the previous tensor stopped, so CTAs stay balanced to within one chunk
+// over the whole launch (with a fixed start, the same CTAs would take the extra chunk of all 64 tensors).
+__device__ __forceinline__ int64_t first_chunk(int ti, int64_t n_vec, int unroll) {
+    if (ti == 0) return blockIdx.x;
+    const int64_t per = (int64_t)kThreads * unroll, chunks = (n_vec + per - 1) / per;
+    const int64_t shift = ((int64_t)ti * chunks) % gridDim.x;
+    return ((int64_t)blockIdx.x + gridDim.x - shift) % gridDim.x;
+}
+
 // Batched form (xs != nullptr): n_tensors tensors of n_vec vectors each, walked IN ORDER by every CTA (grid-stride inside
 // each tensor), so the whole grid streams through one tensor at a time exactly like n separate launches would, without the
 // launch gaps.  Entry i of absmax_bits / scale_out / scale_f32_out belongs to tensor i.
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __re
     for (int ti = 0; ti < n_tensors; ++ti) {
         const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
         uint32_t m = 0;
-        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
             uint4 v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __res
             if (scale_out) store_scalar<DT>(scale_out, ti, sc.s);
             if (scale_f32_out) scale_f32_out[ti] = round_through<DT>(sc.s);
         }
-        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
             uint4 v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __re
         uint4* ot = cs ? reinterpret_cast<uint4*>(os[ti]) : out;
         ScaleArg<PK> sa;
         sa.load(scale, scale_dtype, ti);
-        for (int64_t i = (int64_t)blockIdx.x * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
+        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
             Raw<kIn> r[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
