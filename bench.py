@@ -242,7 +242,7 @@ def run_c3(args, cfg):
         L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
         if world > 1 and not os.environ.get("KVQ_BENCH_NO_ALLREDUCE"):  # (env: debugging aid, not a valid bench line)
             dist.all_reduce(bits, op=dist.ReduceOp.MAX)  # the only collective on the path
-        L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
+        L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
                                       scales.data_ptr(), None, stream), "kvq_quant_batched")
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("KVQ_LIB", os.path.join(_HERE, "libkvq_sm100.so"))
 
 F32, F16, BF16 = 0, 1, 2
 PER_TENSOR, PER_TOKEN = 0, 1
+ABSMAX_COVERS_INPUT = 0x100  # OR into granularity / bits when absmax is the phase-1 result of the same data
 SLIDING, PREFIX_WINDOW, STRIDED, BLOCK, BUDGET = 0, 1, 2, 3, 4
 
 DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}

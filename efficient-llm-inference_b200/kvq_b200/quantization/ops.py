@@ -60,8 +60,8 @@ def quantize_int8_per_tensor(x: torch.Tensor, eps: float = 1e-8, group=None) -> 
         q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
         scale = torch.empty((), dtype=x.dtype, device=x.device)
         sh, st = L.shape_stride(x4)
-        L.check(L.lib().kvq_quant_int8(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(),
-                                       float(eps), q.data_ptr(), None, scale.data_ptr(), None,
+        L.check(L.lib().kvq_quant_int8(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR | L.ABSMAX_COVERS_INPUT,
+                                       bits.data_ptr(), float(eps), q.data_ptr(), None, scale.data_ptr(), None,
                                        L.stream_ptr(x.device)), "kvq_quant_int8")
         L.count_launch()
     return q, scale
@@ -82,8 +82,8 @@ def quantize_int4_per_tensor_packed(x: torch.Tensor, eps: float = 1e-8, group=No
         packed = torch.empty((*x.shape[:-1], (orig_last + 1) // 2), dtype=torch.uint8, device=x.device)
         scale = torch.empty((), dtype=x.dtype, device=x.device)
         sh, st = L.shape_stride(x4)
-        L.check(L.lib().kvq_quant_int4_pack(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(),
-                                            float(eps), packed.data_ptr(), None, scale.data_ptr(), None,
+        L.check(L.lib().kvq_quant_int4_pack(x4.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR | L.ABSMAX_COVERS_INPUT,
+                                            bits.data_ptr(), float(eps), packed.data_ptr(), None, scale.data_ptr(), None,
                                             L.stream_ptr(x.device)), "kvq_quant_int4_pack")
         L.count_launch()
     return packed, scale, orig_last
@@ -189,7 +189,7 @@ def quantize_per_tensor_batched(xs: "TensorTable", codes: "TensorTable", bits: i
         L.check(L.lib().kvq_absmax_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, absmax_bits.data_ptr(), st),
                 "kvq_absmax_batched")
         allreduce_absmax_(absmax_bits, group)
-        L.check(L.lib().kvq_quant_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, int(bits), absmax_bits.data_ptr(),
+        L.check(L.lib().kvq_quant_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, int(bits) | L.ABSMAX_COVERS_INPUT, absmax_bits.data_ptr(),
                                           float(eps), codes.ptrs.data_ptr(), scales.data_ptr(), None, st), "kvq_quant_batched")
         L.count_launch(2)
     return absmax_bits
@@ -265,8 +265,8 @@ class _TokenStore:
         else:
             bits = _absmax_bits(x, L.PER_TOKEN, group)
             fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
-            L.check(fn(x.data_ptr(), dt, sh, st, L.PER_TOKEN, bits.data_ptr(), float(eps), dst.data_ptr(), L.stride3(dst),
-                       sc.data_ptr(), s32.data_ptr(), stream), "kvq_quant (per token)")
+            L.check(fn(x.data_ptr(), dt, sh, st, L.PER_TOKEN | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), float(eps), dst.data_ptr(),
+                       L.stride3(dst), sc.data_ptr(), s32.data_ptr(), stream), "kvq_quant (per token)")
             L.count_launch()
         self.T += n
         self.n_scale_entries += n
@@ -282,8 +282,8 @@ class _TokenStore:
         one32 = torch.empty(1, dtype=torch.float32, device=x.device)
         sh, st = L.shape_stride(x)
         fn = L.lib().kvq_quant_int8 if self.bits == 8 else L.lib().kvq_quant_int4_pack
-        L.check(fn(x.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR, bits.data_ptr(), float(eps), dst.data_ptr(),
-                   L.stride3(dst), one.data_ptr(), one32.data_ptr(), L.stream_ptr(x.device)), "kvq_quant (block)")
+        L.check(fn(x.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), float(eps),
+                   dst.data_ptr(), L.stride3(dst), one.data_ptr(), one32.data_ptr(), L.stream_ptr(x.device)), "kvq_quant (block)")
         L.count_launch()
         self.scales[self.T: self.T + n] = one
         self.scales_f32[self.T: self.T + n] = one32

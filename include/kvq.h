@@ -59,6 +59,13 @@ enum kvq_granularity {
                            calling the helpers on x[:, :, t:t+1, :] (ops.py:323-342) */
 };
 
+/* OR-ed into the `granularity` argument of kvq_quant_int8 / kvq_quant_int4_pack (and into `bits` of kvq_quant_batched):
+ * the caller guarantees that absmax_bits is >= max|x| of the data being quantized -- it is the kvq_absmax result of this
+ * very data, possibly max-combined with other shards.  Then |x / scale| <= qmax (1 + 2^-23), the reference's clamp
+ * (ops.py:29, :50) can never bind, and the kernels skip it (2 of 8 instructions per element).  Without the flag the
+ * clamp is applied, so a smaller, "calibrated" absmax clips exactly like the reference formula would. */
+#define KVQ_ABSMAX_COVERS_INPUT 0x100
+
 /* eviction strategies of src/cache/implementations.py */
 enum kvq_evict_strategy {
     KVQ_EVICT_SLIDING = 0,       /* trim_kv_sliding_window  :124-140 */

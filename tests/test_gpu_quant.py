@@ -149,6 +149,35 @@ def test_batched_multi_tensor_matches_single(kvq, oracle, dtype, bits):
         assert torch.equal(codes[i].cpu(), oq) and bits_equal(scales[i].cpu(), os_) and bits_equal(outs[i].cpu(), want), i
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_calibrated_absmax_clips_like_the_reference_formula(kvq, oracle, dtype):
+    """C ABI called with an absmax SMALLER than max|x| (no KVQ_ABSMAX_COVERS_INPUT flag): clamp(round(x/scale), lo, hi)
+    must clip exactly like the reference formula (ops.py:29, :50) evaluated with that scale."""
+    from kvq_b200 import _lib as L
+    x = gen((2, 4, 33, 64), dtype, 77, outlier=True)
+    xc = x.cuda()
+    half_max = float(x.float().abs().max()) * 0.37
+    bits = torch.tensor([half_max], dtype=torch.float32).view(torch.int32).cuda()
+    half_max = float(bits.view(torch.float32)[0])
+    sh, st = L.shape_stride(xc)
+    q8 = torch.empty(x.shape, dtype=torch.int8, device="cuda")
+    L.check(L.lib().kvq_quant_int8(xc.data_ptr(), L.dtype_code(dtype), sh, st, L.PER_TENSOR, bits.data_ptr(), 1e-8, q8.data_ptr(), None,
+                                   None, None, L.stream_ptr(xc.device)), "kvq_quant_int8")
+    want8, _ = oracle.quantize_int8_per_tensor(x, absmax_override=half_max)
+    assert torch.equal(q8.cpu(), want8) and int(want8.max()) == 127 and int(want8.min()) == -127
+    p4 = torch.empty((2, 4, 33, 32), dtype=torch.uint8, device="cuda")
+    L.check(L.lib().kvq_quant_int4_pack(xc.data_ptr(), L.dtype_code(dtype), sh, st, L.PER_TENSOR, bits.data_ptr(), 1e-8, p4.data_ptr(),
+                                        None, None, None, L.stream_ptr(xc.device)), "kvq_quant_int4_pack")
+    want4, _, _ = oracle.quantize_int4_per_tensor_packed(x, absmax_override=half_max)
+    assert torch.equal(p4.cpu(), want4)
+    # strided view -> rows kernel, same contract
+    xv = xc.transpose(1, 2).contiguous().transpose(1, 2)
+    shv, stv = L.shape_stride(xv)
+    L.check(L.lib().kvq_quant_int8(xv.data_ptr(), L.dtype_code(dtype), shv, stv, L.PER_TENSOR, bits.data_ptr(), 1e-8, q8.data_ptr(), None,
+                                   None, None, L.stream_ptr(xc.device)), "kvq_quant_int8")
+    assert torch.equal(q8.cpu(), want8)
+
+
 def test_kvq_ext_facade(kvq, oracle):
     ext = kvq.get_cuda_extension()
     q = torch.randint(-127, 128, (3, 5, 16), dtype=torch.int8)
