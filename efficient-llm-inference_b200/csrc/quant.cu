@@ -43,7 +43,9 @@ template <int BITS> __device__ __forceinline__ Scale scale_from_bits(uint32_t ab
 
 // float bits of clamp(x/scale) + magic: the low byte (BITS=8) is the int8 code, the low nibble
 // (BITS=4) is code+8.
-template <int DT, int BITS> __device__ __forceinline__ uint32_t code_word(float x, const Scale& sc) {
+// CLAMP = false: the caller guarantees max|x| <= the absmax the scale came from (it is the phase-1 result of this
+// very data, possibly max-combined with other shards), so |x/scale| <= qmax * (1 + 2^-23) and the clamp is dead code.
+template <int DT, int BITS, bool CLAMP = true> __device__ __forceinline__ uint32_t code_word(float x, const Scale& sc) {
     float q;
     if (DT == KVQ_F32) {
         q = __fdiv_rn(x, sc.s);
@@ -52,7 +54,7 @@ template <int DT, int BITS> __device__ __forceinline__ uint32_t code_word(float 
         const float r = __fmaf_rn(-q0, sc.s, x);
         q = __fmaf_rn(r, sc.y, q0);
     }
-    q = fminf(fmaxf(q, Q<BITS>::lo), Q<BITS>::hi);
+    if (CLAMP) q = fminf(fmaxf(q, Q<BITS>::lo), Q<BITS>::hi);
     return __float_as_uint(__fadd_rn(q, Q<BITS>::magic));
 }
 
@@ -94,21 +96,21 @@ template <int DT> struct InVec {
 };
 
 // codes of one input vector, stored at `out` (naturally aligned): kN bytes (INT8) or kN/2 bytes (INT4)
-template <int DT, int BITS> __device__ __forceinline__ void quant_store(const uint4& v, const Scale& sc, void* out) {
+template <int DT, int BITS, bool CLAMP = true> __device__ __forceinline__ void quant_store(const uint4& v, const Scale& sc, void* out) {
     constexpr int kN = InVec<DT>::kN;
     float f[kN];
     InVec<DT>::widen(v, f);
     if constexpr (BITS == 8) {
         uint32_t c[kN];
 #pragma unroll
-        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8>(f[i], sc);
+        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8, CLAMP>(f[i], sc);
         if constexpr (kN == 8) st_stream8(out, make_uint2(pack4_bytes(c[0], c[1], c[2], c[3]), pack4_bytes(c[4], c[5], c[6], c[7])));
         else st_stream4(out, pack4_bytes(c[0], c[1], c[2], c[3]));
     } else {
         uint32_t b[kN / 2];
 #pragma unroll
         for (int i = 0; i < kN / 2; ++i)
-            b[i] = code_word<DT, 4>(f[2 * i], sc) * 16u + code_word<DT, 4>(f[2 * i + 1], sc);  // low byte valid
+            b[i] = code_word<DT, 4, CLAMP>(f[2 * i], sc) * 16u + code_word<DT, 4, CLAMP>(f[2 * i + 1], sc);  // low byte valid
         if constexpr (kN == 8) st_stream4(out, pack4_bytes(b[0], b[1], b[2], b[3]));
         else *reinterpret_cast<unsigned short*>(out) = (unsigned short)(__byte_perm(b[0], b[1], 0x0040) & 0xffffu);
     }
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __re
     }
 }
 
-template <int DT, int BITS, int UNROLL>
+template <int DT, int BITS, int UNROLL, bool CLAMP>
 __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
                                                               const uint32_t* __restrict__ absmax_bits, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __res
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int64_t j = i + (int64_t)u * kThreads;
-                if (j < n_vec) quant_store<DT, BITS>(v[u], sc, qt + j * kOut);
+                if (j < n_vec) quant_store<DT, BITS, CLAMP>(v[u], sc, qt + j * kOut);
             }
         }
     }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) absmax_rows_kernel(const char* __res
     if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits, m);
 }
 
-template <int DT, int BITS, int UNROLL>
+template <int DT, int BITS, int UNROLL, bool CLAMP>
 __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __restrict__ x, RowGeom g,
                                                               const uint32_t* __restrict__ absmax_bits,
                                                               int per_token, float eps, char* __restrict__ q,
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __rest
                 for (int u = 0; u < UNROLL; ++u) {
                     if (tb + r0 + u * rpp >= g.T) continue;
                     if (per_token) { const float2 s2 = tile_scale[r0 + u * rpp]; sc.s = s2.x; sc.y = s2.y; }
-                    quant_store<DT, BITS>(v[u], sc, qout + u * out_step);
+                    quant_store<DT, BITS, CLAMP>(v[u], sc, qout + u * out_step);
                 }
             }
         }
@@ -366,13 +368,13 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
             if (NV > 0) {
 #pragma unroll
                 for (int k = 0; k < kNV; ++k)
-                    if (xoff[k] != kNone) quant_store<DT, BITS>(v[k], sc, qt + qoff[k]);
+                    if (xoff[k] != kNone) quant_store<DT, BITS, kFusedClamp>(v[k], sc, qt + qoff[k]);
             } else {
                 for (int j = threadIdx.x; j < n_vec; j += kThreads) {
                     const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
                     int64_t xo, qo;
                     plane_offsets(g, p, xo, qo);
-                    quant_store<DT, BITS>(ld_stream(xt + xo + (int64_t)c * 16), sc, qt + qo + (int64_t)c * kOut);
+                    quant_store<DT, BITS, kFusedClamp>(ld_stream(xt + xo + (int64_t)c * 16), sc, qt + qo + (int64_t)c * kOut);
                 }
             }
         }
@@ -700,6 +702,8 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
                  const uint32_t* absmax_bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
                  float* scale_f32_out, cudaStream_t st) {
     KVQ_REQUIRE(x && q && absmax_bits && shape && stride, "null pointer");
+    const bool covers = (granularity & KVQ_ABSMAX_COVERS_INPUT) != 0;
+    granularity &= ~KVQ_ABSMAX_COVERS_INPUT;
     KVQ_REQUIRE(granularity == KVQ_PER_TENSOR || granularity == KVQ_PER_TOKEN, "bad granularity %d", granularity);
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     const View4 v = make_view(shape, stride);
@@ -716,13 +720,23 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
         codes_ok(q, qs, piece)) {
         const int64_t n_vec = n * es / 16;
         constexpr int U = 4;
-        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
-                                   (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+        if (covers) {
+            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, false><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
+                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+        } else {
+            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, true><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
+                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+        }
     } else if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece)) {
         const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
         constexpr int U = 4;
-        KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U><<<row_grid_planes_inside(g, U), kThreads, 0, st>>>(
-                                   (const char*)x, g, absmax_bits, per_token, eps, (char*)q, scale_out, scale_f32_out));
+        if (covers) {
+            KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U, false><<<row_grid_planes_inside(g, U), kThreads, 0, st>>>(
+                                       (const char*)x, g, absmax_bits, per_token, eps, (char*)q, scale_out, scale_f32_out));
+        } else {
+            KVQ_DISPATCH_DT(dtype, quant_rows_kernel<DT, BITS, U, true><<<row_grid_planes_inside(g, U), kThreads, 0, st>>>(
+                                       (const char*)x, g, absmax_bits, per_token, eps, (char*)q, scale_out, scale_f32_out));
+        }
     } else {
         const GenGeom g = gen_geom(v, qs);
         KVQ_DISPATCH_DT(dtype, quant_generic_kernel<DT, BITS><<<gen_grid(v.B * v.H * v.T * W), kThreads, 0, st>>>(
@@ -940,6 +954,8 @@ extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_ten
                                  kvq_stream_t stream) {
     KVQ_REQUIRE(xs && qs && absmax_bits, "null pointer");
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
+    const bool covers = (bits & KVQ_ABSMAX_COVERS_INPUT) != 0;
+    bits &= ~KVQ_ABSMAX_COVERS_INPUT;
     KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4");
     KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -948,13 +964,11 @@ extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_ten
     KVQ_REQUIRE((numel * es) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
     const int64_t n_vec = numel * es / 16;
     constexpr int U = 4;
-    if (bits == 8) {
-        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, 8, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(
-                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors));
-    } else {
-        KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, 4, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(
-                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors));
-    }
+#define KVQ_QB(BITS, CL) KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, CL><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>( \
+                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors))
+    if (bits == 8) { if (covers) { KVQ_QB(8, false); } else { KVQ_QB(8, true); } }
+    else { if (covers) { KVQ_QB(4, false); } else { KVQ_QB(4, true); } }
+#undef KVQ_QB
     return check_launch("quant_batched");
 }
 
