@@ -815,17 +815,39 @@ __global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams 
     }
 }
 
+// Optional exact "current token" (the reference's decode step sees the new token's K/V unquantized:
+// benchmarker.py:473-477 concatenates them inside the model before they are quantized at :486): it is merged here
+// as one more split with m = q.k_cur * scale, l = 1, acc = v_cur.
+struct CurToken {
+    const void* q; const void* k; const void* v;  // q [B,Hq,D]; k, v [B,H,D]; all of dtype `dtype`
+    int dtype, G;
+    float qk_scale_log2;
+};
+
 template <int ODT>
 __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
-                                         void* __restrict__ out) {
+                                         void* __restrict__ out, CurToken cur) {
+    __shared__ float dot_s[4];
+    const int64_t hq = blockIdx.x;
+    const int d = threadIdx.x;  // blockDim.x == D (64 or 128)
+    float s_cur = -INFINITY, v_cur = 0.f;
+    if (cur.k) {  // independent of the split kernel: runs before the dependency wait
+        const int64_t kv_row = (hq / cur.G);  // (b * Hq + hq_in) / G == b * H + h  because Hq = G * H
+        float p = load_scale(cur.q, cur.dtype, hq * D + d) * load_scale(cur.k, cur.dtype, kv_row * D + d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if ((d & 31) == 0) dot_s[d >> 5] = p;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w = 0; w < D / 32; ++w) tot += dot_s[w];
+        s_cur = tot * cur.qk_scale_log2;
+        v_cur = load_scale(cur.v, cur.dtype, kv_row * D + d);
+    }
     // launched with programmatic stream serialization: everything above this line overlaps the split kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int64_t hq = blockIdx.x;
-    const int d = threadIdx.x;
-    if (d >= D) return;
     const float2* ml = reinterpret_cast<const float2*>(ws_ml) + hq * n_splits;
     const float* acc = ws_acc + hq * n_splits * D + d;
-    float M = -INFINITY, num = 0.f, den = 0.f;
+    float M = s_cur, num = cur.k ? v_cur : 0.f, den = cur.k ? 1.f : 0.f;
     for (int s0 = 0; s0 < n_splits; s0 += 8) {  // 8 splits per round: independent loads, then an online-softmax merge
         float2 m8[8];
         float a8[8];
@@ -851,14 +873,15 @@ __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const
 }
 
 template <int ODT>
-int launch_merge(unsigned blocks, unsigned threads, cudaStream_t st, const float* ws_acc, const float* ws_ml, int n_splits, int D, void* out) {
+int launch_merge(unsigned blocks, unsigned threads, cudaStream_t st, const float* ws_acc, const float* ws_ml, int n_splits, int D, void* out,
+                 const CurToken& cur) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    KVQ_CUDA(cudaLaunchKernelEx(&cfg, decode_attn_merge_kernel<ODT>, ws_acc, ws_ml, n_splits, D, out));
+    KVQ_CUDA(cudaLaunchKernelEx(&cfg, decode_attn_merge_kernel<ODT>, ws_acc, ws_ml, n_splits, D, out, cur));
     return KVQ_OK;
 }
 
@@ -944,6 +967,16 @@ extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, 
                                const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
                                const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
                                void* out, int out_dtype, void* workspace, int n_splits, kvq_stream_t stream) {
+    return kvq_decode_attn_ex(q, q_dtype, k_codes, k_bits, k_stride3, k_scale, v_codes, v_bits, v_stride3, v_scale, B, Hq, H, T, D,
+                              sm_scale, nullptr, nullptr, out, out_dtype, workspace, n_splits, stream);
+}
+
+extern "C" int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                                  const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                                  const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                                  const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
+                                  kvq_stream_t stream) {
+    KVQ_REQUIRE((k_cur == nullptr) == (v_cur == nullptr), "k_cur and v_cur must be given together");
     KVQ_REQUIRE(q && k_codes && v_codes && k_scale && v_scale && out && workspace, "null pointer");
     KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
     KVQ_REQUIRE((k_bits == 8 || k_bits == 4) && (v_bits == 8 || v_bits == 4), "k_bits / v_bits must be 8 or 4");
@@ -987,10 +1020,11 @@ extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, 
     rc = check_launch("decode_attn_split");
     if (rc != KVQ_OK) return rc;
     const unsigned mt = (unsigned)D;
+    const CurToken cur{q, k_cur, v_cur, q_dtype, G, P.qk_scale_log2};
     switch (out_dtype) {
-        case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
-        case KVQ_F16: rc = launch_merge<KVQ_F16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
-        default: rc = launch_merge<KVQ_BF16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out); break;
+        case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
+        case KVQ_F16: rc = launch_merge<KVQ_F16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
+        default: rc = launch_merge<KVQ_BF16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
     }
     if (rc != KVQ_OK) return rc;
     return check_launch("decode_attn_merge");

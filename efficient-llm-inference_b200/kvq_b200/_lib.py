@@ -64,6 +64,8 @@ SIGNATURES = {
     "kvq_paged_gather": (c_int, [c_vp, c_int, I64x4, c_vp, c_i64, c_vp, c_vp]),
     "kvq_chunk_mean": (c_int, [c_vp, c_int, I64x4, I64x4, c_i64, c_i64, c_vp, c_vp]),
     "kvq_decode_attn_workspace_bytes": (c_i64, [c_i64] * 5 + [ctypes.POINTER(c_int)]),
+    "kvq_decode_attn_ex": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
+                           + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     "kvq_decode_attn": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
                         + [c_f, c_vp, c_int, c_vp, c_int, c_vp]),
 }

@@ -20,11 +20,14 @@ from . import _lib as L
 def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales: torch.Tensor, k_bits: int,
                                v_codes: torch.Tensor, v_scales: torch.Tensor, v_bits: int,
                                sm_scale: Optional[float] = None, out_dtype: Optional[torch.dtype] = None,
-                               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               workspace: Optional[torch.Tensor] = None, k_cur: Optional[torch.Tensor] = None,
+                               v_cur: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b,hq] = softmax_t(q[b,hq] . K[b,hq//G,t] * sm_scale) @ V[b,hq//G]  with K/V = codes * scale[t].
 
     q [B,Hq,1,D] (fp32/fp16/bf16); k_codes int8 [B,H,T,D] (k_bits 8) or uint8 [B,H,T,D/2] (k_bits 4);
     k_scales fp32 [T]; v likewise.  G = Hq/H in {1,2,4,8}; D in {64,128}.  Returns [B,Hq,1,D].
+    k_cur / v_cur (optional, [B,H,1,D]): the decode step's own token, attended to exactly (unquantized) on top
+    of the T cached tokens, as the reference's loop does.
     """
     L.require_cuda(q, k_codes, v_codes, k_scales, v_scales)
     if q.dim() != 4 or q.size(2) != 1:
@@ -41,6 +44,13 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
         sm_scale = float(D) ** -0.5
     out_dtype = out_dtype or q.dtype
     qc = q.contiguous()
+    if (k_cur is None) != (v_cur is None):
+        raise RuntimeError("k_cur and v_cur must be given together")
+    if k_cur is not None:
+        L.require_cuda(k_cur, v_cur)
+        if tuple(k_cur.shape) != (B, H, 1, D) or tuple(v_cur.shape) != (B, H, 1, D):
+            raise RuntimeError("k_cur / v_cur must be [B, H, 1, D]")
+        k_cur, v_cur = k_cur.to(q.dtype).contiguous(), v_cur.to(q.dtype).contiguous()
     k_scales, v_scales = k_scales.contiguous(), v_scales.contiguous()
     out = torch.empty((B, Hq, 1, D), dtype=out_dtype, device=q.device)
     with L.device_guard(q):
@@ -48,10 +58,12 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
         nbytes = L.lib().kvq_decode_attn_workspace_bytes(B, Hq, H, T, D, ctypes.byref(ns))
         if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
             workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=q.device)
-        L.check(L.lib().kvq_decode_attn(qc.data_ptr(), L.dtype_code(q.dtype), k_codes.data_ptr(), int(k_bits),
-                                        L.stride3(k_codes), k_scales.data_ptr(), v_codes.data_ptr(), int(v_bits),
-                                        L.stride3(v_codes), v_scales.data_ptr(), B, Hq, H, T, D, float(sm_scale),
-                                        out.data_ptr(), L.dtype_code(out_dtype), workspace.data_ptr(), ns.value,
-                                        L.stream_ptr(q.device)), "kvq_decode_attn")
+        L.check(L.lib().kvq_decode_attn_ex(qc.data_ptr(), L.dtype_code(q.dtype), k_codes.data_ptr(), int(k_bits),
+                                           L.stride3(k_codes), k_scales.data_ptr(), v_codes.data_ptr(), int(v_bits),
+                                           L.stride3(v_codes), v_scales.data_ptr(), B, Hq, H, T, D, float(sm_scale),
+                                           k_cur.data_ptr() if k_cur is not None else None,
+                                           v_cur.data_ptr() if v_cur is not None else None,
+                                           out.data_ptr(), L.dtype_code(out_dtype), workspace.data_ptr(), ns.value,
+                                           L.stream_ptr(q.device)), "kvq_decode_attn")
         L.count_launch(2)
     return out

@@ -1,0 +1,147 @@
+"""A `transformers` cache whose layers are quantized stores, plus the attention function that reads them
+fused ("next" row 1).
+
+The reference's quantized decode loop dequantizes the WHOLE cache every step, wraps it in a DynamicCache and
+lets the model concatenate the new token and run attention on fp tensors
+(/root/reference/src/benchmarking/benchmarker.py:465-486, src/quantization/ops.py:213-269, :345-355): O(T) bytes
+written and re-read per step just to feed attention.  Here the model talks to the quantized store directly:
+
+  * `KvqFusedCache.update()` (called by every attention layer) quantizes and appends the incoming tokens with
+    one scale per token -- exactly what `QuantizedKVCache.init_from_prompt_past` / `append_from_past` do -- and
+    hands the layer only the tokens it was given;
+  * prefill (more than one query token) attends over those exact prompt tokens with the model's stock
+    attention, like the reference's first forward;
+  * a decode step (one query token) calls the fused kernel: INT8/INT4 codes of the cached tokens are
+    dequantized in registers, the step's own token is attended to exactly (unquantized), as in the reference.
+
+Use `fused_attention(model)` as a context manager: it registers the attention function under the name
+"kvq_fused" and switches `model.config._attn_implementation` to it for the duration.
+"""
+
+from __future__ import annotations
+
+import contextlib
+from typing import Optional, Tuple
+
+import torch
+from transformers.cache_utils import Cache, CacheLayerMixin
+
+from .attention import decode_attention_quantized
+from .quantization.ops import QuantizedLayerKV
+
+ATTN_NAME = "kvq_fused"
+
+# the layer whose update() ran last, per layer index: the attention function of the same module call reads it
+_pending = {}
+
+
+class KvqCacheLayer(CacheLayerMixin):
+    """One layer of the cache: a QuantizedLayerKV store (codes + per-token scales on the device)."""
+
+    is_sliding = False
+
+    def __init__(self, layer_idx: int, mode: str, compute_dtype: torch.dtype, group=None):
+        super().__init__()
+        self.layer_idx = layer_idx
+        self.mode = mode
+        self.store = QuantizedLayerKV(mode=mode, device="cuda", compute_dtype=compute_dtype, group=group)
+        self.cached_before_update = 0
+
+    def lazy_initialization(self, key_states: torch.Tensor, value_states: torch.Tensor) -> None:
+        self.dtype, self.device = key_states.dtype, key_states.device
+        self.is_initialized = True
+
+    def update(self, key_states: torch.Tensor, value_states: torch.Tensor, *args, **kwargs
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        if not self.is_initialized:
+            self.lazy_initialization(key_states, value_states)
+        self.cached_before_update = len(self.store)
+        self.store.append_tokens(key_states, value_states)  # one scale per token, one launch per tensor
+        _pending[self.layer_idx] = self
+        return key_states, value_states                     # only the new tokens: the rest stays quantized
+
+    def get_seq_length(self) -> int:
+        return len(self.store)
+
+    def get_mask_sizes(self, query_length: int) -> Tuple[int, int]:
+        return self.get_seq_length() + query_length, 0
+
+    def get_max_cache_shape(self) -> int:
+        return -1
+
+    # the store is not a pair of fp tensors: operations that assume so are not supported
+    def offload(self):
+        raise NotImplementedError("KvqCacheLayer keeps its codes on the GPU")
+
+    def prefetch(self):
+        return None
+
+    def reset(self) -> None:
+        self.store = QuantizedLayerKV(mode=self.mode, device="cuda", compute_dtype=self.store.compute_dtype, group=self.store.group)
+
+    def reorder_cache(self, beam_idx):
+        raise NotImplementedError("beam search is not supported on the quantized store")
+
+
+class KvqFusedCache(Cache):
+    """`past_key_values` object backed by quantized stores (modes "int8", "int4", "mixed")."""
+
+    def __init__(self, n_layers: int, mode: str = "int8", compute_dtype: torch.dtype = torch.float16, group=None):
+        assert mode in ["int8", "int4", "mixed"], f"Invalid mode: {mode}"
+        super().__init__(layers=[KvqCacheLayer(i, mode, compute_dtype, group) for i in range(n_layers)])
+        self.mode = mode
+
+    def estimated_bytes(self) -> int:
+        """Same accounting as QuantizedKVCache.estimated_bytes (reference ops.py:357-363)."""
+        return sum(layer.store.estimated_bytes() for layer in self.layers)
+
+    def to_past_key_values(self) -> tuple:
+        """Dequantized ((k, v), ...) like QuantizedKVCache.to_past_key_values, for inspection."""
+        return tuple(layer.store.get_kv() for layer in self.layers)
+
+
+def kvq_fused_attention(module, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
+                        attention_mask: Optional[torch.Tensor], dropout: float = 0.0, scaling: Optional[float] = None,
+                        **kwargs):
+    """Attention function registered under "kvq_fused" (transformers AttentionInterface signature).
+
+    query [B,Hq,q_len,D]; key / value are what KvqCacheLayer.update returned: the new tokens only."""
+    layer = _pending.pop(getattr(module, "layer_idx", None), None)
+    q_len = query.size(2)
+    if layer is None or q_len != 1 or layer.cached_before_update == 0 or key.size(2) != 1:
+        # prefill (or a module without our cache): stock attention over the tokens at hand
+        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+        return ALL_ATTENTION_FUNCTIONS["sdpa"](module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
+    T = layer.cached_before_update
+    kc, ks, kb, vc, vs, vb = layer.store.quantized()
+    out = decode_attention_quantized(query, kc[:, :, :T], ks[:T], kb, vc[:, :, :T], vs[:T], vb, sm_scale=scaling,
+                                     out_dtype=query.dtype, k_cur=key, v_cur=value)
+    return out.transpose(1, 2), None  # [B, 1, Hq, D], like the stock attention functions
+
+
+def register() -> None:
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    try:
+        from transformers import AttentionInterface
+        AttentionInterface.register(ATTN_NAME, kvq_fused_attention)
+    except Exception:
+        ALL_ATTENTION_FUNCTIONS[ATTN_NAME] = kvq_fused_attention
+    try:  # the causal-mask builder is looked up under the same name: reuse the sdpa one
+        from transformers import AttentionMaskInterface
+        from transformers.masking_utils import sdpa_mask
+        AttentionMaskInterface.register(ATTN_NAME, sdpa_mask)
+    except Exception:
+        pass
+
+
+@contextlib.contextmanager
+def fused_attention(model):
+    """Route `model`'s attention through the quantized store for the duration of the block."""
+    register()
+    old = model.config._attn_implementation
+    model.config._attn_implementation = ATTN_NAME
+    try:
+        yield
+    finally:
+        model.config._attn_implementation = old
+        _pending.clear()

@@ -243,6 +243,15 @@ KVQ_API int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, int
                     const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
                     void* out, int out_dtype, void* workspace, int n_splits, kvq_stream_t stream);
 
+/* kvq_decode_attn plus the decode step's own token, exact: k_cur / v_cur are [B, H, D] of q's dtype (both NULL = plain
+ * kvq_decode_attn).  The reference's step attends over dequant(cached tokens) ++ the new token's unquantized K/V
+ * (benchmarker.py:473-477) and only then quantizes it (:486); the new token enters the softmax merge as one more split. */
+KVQ_API int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                               const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                               const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                               const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
+                               kvq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

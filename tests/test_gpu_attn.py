@@ -86,3 +86,25 @@ def test_bad_arguments(kvq):
     kc = torch.zeros(1, 1, 4, 64, dtype=torch.int8, device="cuda")
     with pytest.raises(RuntimeError, match="Hq/H"):
         kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)
+
+
+def test_exact_current_token_merge(kvq, oracle):
+    """kvq_decode_attn_ex: cached tokens from codes + the step's own token unquantized (what the reference's decode step
+    attends to, benchmarker.py:473-477).  Expected = fp32 attention over [dequant(cached) ++ exact current]."""
+    for (B, Hq, H, T, D, mode) in [(2, 4, 4, 300, 64, "mixed"), (1, 8, 2, 257, 128, "int8"), (2, 12, 12, 130, 64, "int4"), (1, 2, 2, 1, 128, "mixed")]:
+        g = torch.Generator().manual_seed(T)
+        k, v = torch.randn(B, H, T, D, generator=g), torch.randn(B, H, T, D, generator=g)
+        q = torch.randn(B, Hq, 1, D, generator=g)
+        kcur, vcur = torch.randn(B, H, 1, D, generator=g) * 2, torch.randn(B, H, 1, D, generator=g)
+        layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float32)
+        layer.append_tokens(k.cuda(), v.cuda())
+        kc, ks, kb, vc, vs, vb = layer.quantized()
+        kd = oracle.dequantize_per_token(kc.cpu(), kb, ks.cpu(), D, torch.float32)
+        vd = oracle.dequantize_per_token(vc.cpu(), vb, vs.cpu(), D, torch.float32)
+        G = Hq // H
+        kk = torch.cat([kd, kcur], 2).repeat_interleave(G, 1).double()
+        vv = torch.cat([vd, vcur], 2).repeat_interleave(G, 1).double()
+        w = torch.softmax(torch.matmul(q.double(), kk.transpose(-1, -2)) * D ** -0.5, -1)
+        want = torch.matmul(w, vv).float()
+        got = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb, k_cur=kcur.cuda(), v_cur=vcur.cuda())
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)

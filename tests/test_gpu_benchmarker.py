@@ -91,3 +91,39 @@ def test_batch16_quant_mixed_with_window(bench):
     assert r["total_new_tokens"] == 4 and r["est_kv_cache_mb_avg"] > 0
     r = b16.benchmark_method([PROMPT], method="sliding_window", max_new_tokens=4, window_size=32)
     assert r["total_new_tokens"] == 4
+
+
+def test_fused_attention_cache_matches_dequantize_path(bench):
+    """KvqFusedCache + fused decode attention vs the reference-style loop (dequantize everything, DynamicCache): same
+    quantized store (codes and scales bit-identical), next-token logits within fp16 noise, same cache size."""
+    from kvq_b200.hf_cache import KvqFusedCache, fused_attention
+    from kvq_b200.quantization import QuantizedKVCache
+    from transformers import DynamicCache
+    model = bench.model
+    ids = StubTokenizer()(PROMPT).input_ids.cuda()
+    for mode in ("int8", "mixed"):
+        # reference-style: prefill, quantize the prompt, one step on the dequantized cache
+        out = model(input_ids=ids, use_cache=True)
+        kv = tuple((l.keys, l.values) for l in out.past_key_values.layers)
+        qc = QuantizedKVCache(n_layers=len(kv), mode=mode, device="cuda", compute_dtype=torch.float16)
+        qc.init_from_prompt_past(kv)
+        nxt = torch.argmax(out.logits[:, -1, :], dim=-1, keepdim=True)
+        ref = model(input_ids=nxt, use_cache=True, past_key_values=DynamicCache(ddp_cache_data=qc.to_past_key_values()))
+        # fused: the model writes into / reads from the quantized store
+        cache = KvqFusedCache(len(kv), mode=mode, compute_dtype=torch.float16)
+        with fused_attention(model):
+            out2 = model(input_ids=ids, use_cache=True, past_key_values=cache)
+            assert torch.equal(torch.argmax(out2.logits[:, -1, :], -1, keepdim=True), nxt)
+            for a, b in zip(cache.layers, qc.layers):  # identical stores after the prompt
+                assert torch.equal(a.store.quantized()[0], b.quantized()[0]) and torch.equal(a.store.quantized()[3], b.quantized()[3])
+                assert torch.equal(a.store.quantized()[1], b.quantized()[1])
+            got = model(input_ids=nxt, use_cache=True, past_key_values=cache)
+        assert cache.get_seq_length() == ids.size(1) + 1
+        torch.testing.assert_close(got.logits.float(), ref.logits.float(), rtol=2e-2, atol=2e-2)
+    t_fused = bench.generate_with_quantized_kv(PROMPT, 8, mode="int8", fused_attention=True)
+    t_plain = bench.generate_with_quantized_kv(PROMPT, 8, mode="int8")
+    assert t_fused[1] == t_plain[1] == 8 and t_fused[2] == t_plain[2]
+    agree = sum(a == b for a, b in zip(t_fused[0].split(), t_plain[0].split())) / len(t_plain[0].split())
+    assert agree >= 0.95  # random-init logits are nearly flat: allow an occasional argmax flip late in the sequence
+    r = bench.benchmark_method([PROMPT], method="quant_mixed", max_new_tokens=4, fused_attention=True)
+    assert r["total_new_tokens"] == 4 and r["est_kv_cache_mb_avg"] > 0
