@@ -72,3 +72,27 @@ def test_benchmarker_method_table():
                  "generate_with_quantized_kv", "generate_with_paged_attention", "generate_with_chunked_cache",
                  "benchmark_method"):
         assert callable(getattr(b, name))
+
+
+def test_reference_import_root_alias():
+    """`src.*` imports of code written against the reference resolve to this package (drop-in import root)."""
+    import importlib
+    import subprocess
+    import sys
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "efficient-llm-inference_b200")
+    code = ("from src.quantization import QuantizedKVCache, quantize_int8_per_tensor, dequantize_int4_per_tensor_packed\n"
+            "from src.quantization.ops import QuantizedLayerKV\n"
+            "from src.cache import trim_kv_strided, PagedKVCache, chunk_summarize_kv, trim_kv_budget_old\n"
+            "from src.cache.implementations import trim_kv_block_old\n"
+            "from src.cuda import get_cuda_extension, build_cuda_extension\n"
+            "from src.core import Config, CacheConfig, mb\n"
+            "from src.benchmarking import KVCacheBenchmarker\n"
+            "from src.benchmarking.benchmarker import KVCacheBenchmarker as K2\n"
+            "import src, kvq_b200\n"
+            "assert QuantizedKVCache is kvq_b200.QuantizedKVCache and K2 is KVCacheBenchmarker\n"
+            "try:\n    from src import MMLUBenchmark\n    raise SystemExit(1)\nexcept ImportError:\n    pass\n"
+            "print('ok')")
+    env = {**os.environ, "PYTHONPATH": root}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-800:]
