@@ -167,7 +167,7 @@ class KVCacheBenchmarker:
 
     @torch.no_grad()
     def generate_with_quantized_kv(self, prompt: str, max_new_tokens: int = 32, mode: str = "int8",
-                                   fused_attention: bool = False) -> Tuple[str, int, float]:
+                                   fused_attention: bool = False, evict: Optional[dict] = None) -> Tuple[str, int, float]:
         """Decode with the KV cache stored quantized (int8 / int4 / mixed).  Returns (text, n_new, cache MB).
 
         Prompt: one fused absmax+quantize launch per layer tensor (one scale per token).  Each step: one
@@ -175,10 +175,14 @@ class KVCacheBenchmarker:
 
         fused_attention=True (not in the reference): the model reads the quantized store directly through
         `KvqFusedCache` and the fused dequant decode-attention kernel instead of dequantizing the whole cache into
-        a DynamicCache every step (kvq_b200/hf_cache.py); same cache contents, same per-token scales."""
+        a DynamicCache every step (kvq_b200/hf_cache.py); same cache contents, same per-token scales.
+        evict (with fused_attention): a QuantizedLayerKV.evict() keyword dict, e.g. {"strategy": "sliding_window",
+        "window_size": 256}: quantization composed with an eviction strategy in one cache (BASELINE config C2)."""
         ids = self._encode(prompt, False)
         if fused_attention:
-            return self._generate_fused(ids, max_new_tokens, mode)
+            return self._generate_fused(ids, max_new_tokens, mode, evict)
+        if evict is not None:
+            raise ValueError("a composed quantize + evict cache needs fused_attention=True (KvqFusedCache)")
         compute_dtype = torch.float16 if str(self.device).startswith("cuda") else torch.float32
         state = {}
 
@@ -197,12 +201,13 @@ class KVCacheBenchmarker:
         return text, n_new, mb(state["q"].estimated_bytes())
 
     @torch.no_grad()
-    def _generate_fused(self, ids: torch.Tensor, max_new_tokens: int, mode: str) -> Tuple[str, int, float]:
+    def _generate_fused(self, ids: torch.Tensor, max_new_tokens: int, mode: str, evict: Optional[dict] = None
+                        ) -> Tuple[str, int, float]:
         from ..hf_cache import KvqFusedCache, fused_attention
         cfg = self.model.config
         n_layers = getattr(cfg, "num_hidden_layers", None) or cfg.n_layer
         dtype = next(self.model.parameters()).dtype
-        cache = KvqFusedCache(n_layers, mode=mode, compute_dtype=dtype)
+        cache = KvqFusedCache(n_layers, mode=mode, compute_dtype=dtype, evict=evict)
         with fused_attention(self.model):
             out = self.model(input_ids=ids, use_cache=True, past_key_values=cache)
             logits = out.logits[:, -1, :]
@@ -259,7 +264,7 @@ class KVCacheBenchmarker:
     def benchmark_method(self, prompts: list, method: str = "no_cache", max_new_tokens: int = 32, window_size: int = 256,
                          block_size: int = 64, chunk_size: int = 64, keep_last: int = 256, mode: str = "int8",
                          prefix_len: int = 32, stride: int = 4, keep_per_block: int = 8, old_budget: int = 64,
-                         fused_attention: bool = False) -> dict:
+                         fused_attention: bool = False, evict: Optional[dict] = None) -> dict:
         """Run `method` over `prompts` (sequentially) and report time, tokens/s and memory.
         `fused_attention` (extension, default off) applies to the quant_* methods, see generate_with_quantized_kv."""
         assert method in self.VALID_METHODS, f"Invalid method: {method}"
@@ -268,9 +273,9 @@ class KVCacheBenchmarker:
             "no_cache": lambda p: (self.generate_no_cache(p, max_new_tokens)[1], 0.0),
             "full_cache": lambda p: (self.generate_with_cache(p, max_new_tokens)[1], nan),
             "sliding_window": lambda p: (self.generate_with_sliding_window(p, max_new_tokens, window_size=window_size)[1], nan),
-            "quant_int8": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int8", fused_attention=fused_attention)[1:3],
-            "quant_int4": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int4", fused_attention=fused_attention)[1:3],
-            "quant_mixed": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="mixed", fused_attention=fused_attention)[1:3],
+            "quant_int8": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int8", fused_attention=fused_attention, evict=evict)[1:3],
+            "quant_int4": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int4", fused_attention=fused_attention, evict=evict)[1:3],
+            "quant_mixed": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="mixed", fused_attention=fused_attention, evict=evict)[1:3],
             "paged_attention": lambda p: self.generate_with_paged_attention(p, max_new_tokens, block_size=block_size)[1:3],
             "chunked_cache": lambda p: self.generate_with_chunked_cache(p, max_new_tokens, chunk_size=chunk_size,
                                                                         keep_last=keep_last)[1:3],

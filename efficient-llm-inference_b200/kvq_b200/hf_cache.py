@@ -40,10 +40,11 @@ class KvqCacheLayer(CacheLayerMixin):
 
     is_sliding = False
 
-    def __init__(self, layer_idx: int, mode: str, compute_dtype: torch.dtype, group=None):
+    def __init__(self, layer_idx: int, mode: str, compute_dtype: torch.dtype, group=None, evict: Optional[dict] = None):
         super().__init__()
         self.layer_idx = layer_idx
         self.mode = mode
+        self.evict = evict  # e.g. {"strategy": "sliding_window", "window_size": 256}: applied to the store after every step
         self.store = QuantizedLayerKV(mode=mode, device="cuda", compute_dtype=compute_dtype, group=group)
         self.cached_before_update = 0
 
@@ -55,6 +56,10 @@ class KvqCacheLayer(CacheLayerMixin):
                ) -> Tuple[torch.Tensor, torch.Tensor]:
         if not self.is_initialized:
             self.lazy_initialization(key_states, value_states)
+        if self.evict is not None and len(self.store) > 0:
+            # trim what earlier steps accumulated (the reference's loops trim after every step, benchmarker.py:199-205):
+            # doing it here, before the append, keeps `cached_before_update` tokens contiguous for this step's attention
+            self.store.evict(**self.evict)
         self.cached_before_update = len(self.store)
         self.store.append_tokens(key_states, value_states)  # one scale per token, one launch per tensor
         _pending[self.layer_idx] = self
@@ -86,9 +91,12 @@ class KvqCacheLayer(CacheLayerMixin):
 class KvqFusedCache(Cache):
     """`past_key_values` object backed by quantized stores (modes "int8", "int4", "mixed")."""
 
-    def __init__(self, n_layers: int, mode: str = "int8", compute_dtype: torch.dtype = torch.float16, group=None):
+    def __init__(self, n_layers: int, mode: str = "int8", compute_dtype: torch.dtype = torch.float16, group=None,
+                 evict: Optional[dict] = None):
+        """evict (optional): a QuantizedLayerKV.evict() keyword dict, e.g. {"strategy": "sliding_window",
+        "window_size": 256} -- BASELINE config C2's "quant_mixed + sliding_window 256" as ONE cache object."""
         assert mode in ["int8", "int4", "mixed"], f"Invalid mode: {mode}"
-        super().__init__(layers=[KvqCacheLayer(i, mode, compute_dtype, group) for i in range(n_layers)])
+        super().__init__(layers=[KvqCacheLayer(i, mode, compute_dtype, group, evict) for i in range(n_layers)])
         self.mode = mode
 
     def estimated_bytes(self) -> int:

@@ -301,6 +301,26 @@ class _TokenStore:
         L.count_launch()
         return out
 
+    def evict(self, plan, table, kept_idx: torch.Tensor) -> None:
+        """Compact the store to the tokens kept by an eviction plan: codes through the same index-computing gather
+        kernel as fp caches (1-byte elements), scales by the device-computed index list.  With one scale per token this
+        equals quantizing the trimmed fp cache, bit for bit."""
+        from ..cache.implementations import gather_tokens
+        n = int(plan.n_total)
+        live = self.codes[:, :, : self.T]
+        new_codes = gather_tokens(live, plan, table)
+        cap = max(256, 1 << max(n - 1, 0).bit_length())
+        codes = torch.empty((new_codes.size(0), new_codes.size(1), cap, new_codes.size(3)), dtype=self.codes.dtype,
+                            device=self.codes.device)
+        codes[:, :, :n].copy_(new_codes)
+        scales = torch.empty(cap, dtype=self.scales.dtype, device=self.scales.device)
+        s32 = torch.empty(cap, dtype=torch.float32, device=self.scales.device)
+        scales[:n] = self.scales[: self.T].index_select(0, kept_idx)
+        s32[:n] = self.scales_f32[: self.T].index_select(0, kept_idx)
+        self.codes, self.scales, self.scales_f32 = codes, scales, s32
+        self.T = n
+        self.n_scale_entries = n
+
     def nbytes(self) -> int:
         if self.codes is None:
             return 0
@@ -394,6 +414,38 @@ class QuantizedLayerKV:
             raise ValueError("Empty cache")
         with L.device_guard(self._k.codes):
             return self._k.dequantize(self.compute_dtype), self._v.dequantize(self.compute_dtype)
+
+    _STRATEGIES = {"sliding_window": L.SLIDING, "prefix_window": L.PREFIX_WINDOW, "strided": L.STRIDED, "block": L.BLOCK,
+                   "budget": L.BUDGET}
+
+    @torch.no_grad()
+    def evict(self, strategy: str, window_size: int = 256, prefix_len: int = 0, stride: int = 4, block_size: int = 64,
+              keep_per_block: int = 8, old_budget: int = 64) -> int:
+        """Apply one of the reference's eviction strategies (src/cache/implementations.py:124-292, same parameter names
+        as the trim_kv_* functions) directly to the quantized store -- the reference only offers quantization and
+        eviction as separate methods (benchmarker.py:673-686).  Returns the new length.  Composition is exact: with one
+        scale per token, evicting codes equals quantizing the evicted fp cache."""
+        import ctypes
+        from ..cache.implementations import _old_table, evict_plan
+        if strategy not in self._STRATEGIES:
+            raise ValueError(f"unknown eviction strategy {strategy!r}; one of {sorted(self._STRATEGIES)}")
+        T = self._k.T
+        if T == 0:
+            raise ValueError("Empty cache")
+        plan = evict_plan(self._STRATEGIES[strategy], T, window=window_size, prefix=prefix_len, stride=stride, block=block_size,
+                          keep=keep_per_block, budget=old_budget)
+        if plan.identity:
+            return T
+        dev = self._k.codes.device
+        with torch.cuda.device(dev):
+            table = _old_table(plan, dev)
+            kept = torch.empty(int(plan.n_total), dtype=torch.int64, device=dev)
+            L.check(L.lib().kvq_evict_indices_device(ctypes.byref(plan), table.data_ptr() if table is not None else None,
+                                                     kept.data_ptr(), L.stream_ptr(dev)), "kvq_evict_indices_device")
+            L.count_launch()
+            self._k.evict(plan, table, kept)
+            self._v.evict(plan, table, kept)
+        return self._k.T
 
     def quantized(self):
         """(k_codes, k_scales_f32, k_bits, v_codes, v_scales_f32, v_bits) views of the live store, for

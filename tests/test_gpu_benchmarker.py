@@ -127,3 +127,16 @@ def test_fused_attention_cache_matches_dequantize_path(bench):
     assert agree >= 0.95  # random-init logits are nearly flat: allow an occasional argmax flip late in the sequence
     r = bench.benchmark_method([PROMPT], method="quant_mixed", max_new_tokens=4, fused_attention=True)
     assert r["total_new_tokens"] == 4 and r["est_kv_cache_mb_avg"] > 0
+
+
+def test_composed_quant_plus_sliding_window(bench):
+    """BASELINE C2 in miniature: mixed INT8-K / INT4-V store + sliding window in ONE cache object (fused attention)."""
+    ev = {"strategy": "sliding_window", "window_size": 32}
+    text, n_new, est_mb = bench.generate_with_quantized_kv(PROMPT, 6, mode="mixed", fused_attention=True, evict=ev)
+    # the store holds the window (trimmed before each append) + the token of the last step
+    assert n_new == 6 and est_mb == 3 * (4 * 33 * (64 + 32) + 2 * 33 * 2) / 1024 ** 2
+    # a window larger than the sequence changes nothing
+    big = bench.generate_with_quantized_kv(PROMPT, 6, mode="mixed", fused_attention=True, evict={"strategy": "sliding_window", "window_size": 4096})
+    assert big[0] == bench.generate_with_quantized_kv(PROMPT, 6, mode="mixed", fused_attention=True)[0]
+    with pytest.raises(ValueError):
+        bench.generate_with_quantized_kv(PROMPT, 2, mode="mixed", evict=ev)

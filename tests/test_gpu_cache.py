@@ -185,3 +185,30 @@ def test_long_context_properties(kvq, oracle):
     want = k[:, :, : T - 256].double().view(B, H, 2044, 64, D).mean(3)
     torch.testing.assert_close(ck[:, :, :2044].double(), want, rtol=2 ** -7, atol=1e-6)
     assert torch.equal(ck[:, :, 2044:], k[:, :, T - 256:])
+
+
+@pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
+def test_evict_on_quantized_store_equals_quantizing_the_evicted_cache(kvq, oracle, mode):
+    """QuantizedLayerKV.evict(): every strategy applied to the code store == the reference's trim applied to the fp cache
+    followed by per-token quantization (codes and scales bit-identical, so dequantized tensors too)."""
+    x = gen((2, 4, 1100, 64), torch.float16, 31)
+    y = gen((2, 4, 1100, 64), torch.float16, 32)
+    for strat, kw, fn, fkw in (("sliding_window", dict(window_size=256), "trim_kv_sliding_window", dict(window_size=256)),
+                               ("prefix_window", dict(window_size=128, prefix_len=16), "trim_kv_prefix_window", dict(window_size=128, prefix_len=16)),
+                               ("strided", dict(window_size=256, stride=4, prefix_len=2), "trim_kv_strided", dict(window_size=256, stride=4, prefix_len=2)),
+                               ("block", dict(window_size=256, block_size=64, keep_per_block=8), "trim_kv_block_old", dict(window_size=256, block_size=64, keep_per_block=8)),
+                               ("budget", dict(window_size=256, old_budget=64), "trim_kv_budget_old", dict(window_size=256, old_budget=64)),
+                               ("sliding_window", dict(window_size=5000), "trim_kv_sliding_window", dict(window_size=5000))):
+        layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float16)
+        layer.append_tokens(x.cuda(), y.cuda())
+        n = layer.evict(strat, **kw)
+        (tx, ty), = getattr(oracle, fn)(((x, y),), **fkw)
+        assert n == tx.size(2) == len(layer)
+        kb, vb = (4 if mode == "int4" else 8), (8 if mode == "int8" else 4)
+        ok, oks, _ = oracle.quantize_per_token(tx.contiguous(), kb)
+        ov, ovs, _ = oracle.quantize_per_token(ty.contiguous(), vb)
+        kc, ks, _, vc, vs, _ = layer.quantized()
+        assert torch.equal(kc.cpu(), ok) and torch.equal(vc.cpu(), ov), strat
+        assert torch.equal(ks.cpu(), oks.float()) and torch.equal(vs.cpu(), ovs.float()), strat
+        layer.append_tokens(x[:, :, :3].cuda(), y[:, :, :3].cuda())  # the store keeps working after compaction
+        assert len(layer) == n + 3 and layer.estimated_bytes() > 0
