@@ -211,16 +211,28 @@ def dequantize_per_tensor_batched(codes: "TensorTable", bits: int, scales: torch
 class _TokenStore:
     """Codes of one K or V stream: [B,H,cap,W] (W = D for INT8, ceil(D/2) for INT4) plus one scale per
     token in the input dtype (what the reference returns) and the same value widened to fp32 (what the
-    fused attention kernel reads).  Capacity doubles; tokens are contiguous along dim 2."""
+    fused attention kernel reads).  The live tokens are rows [start, start + T) of dim 2, contiguous; capacity
+    doubles; a sliding window only advances `start` (no copy) until the tail of the buffer is reached."""
 
     def __init__(self, bits: int):
         self.bits = bits
         self.codes: Optional[torch.Tensor] = None
         self.scales: Optional[torch.Tensor] = None      # [cap] input dtype
         self.scales_f32: Optional[torch.Tensor] = None  # [cap] fp32
+        self.start = 0
         self.T = 0
         self.D = 0
         self.n_scale_entries = 0  # how many scale tensors the reference would hold (one per append)
+
+    # ---- views of the live region
+    def live_codes(self) -> torch.Tensor:
+        return self.codes[:, :, self.start: self.start + self.T]
+
+    def live_scales(self) -> torch.Tensor:
+        return self.scales[self.start: self.start + self.T]
+
+    def live_scales_f32(self) -> torch.Tensor:
+        return self.scales_f32[self.start: self.start + self.T]
 
     def _reserve(self, x: torch.Tensor, n_new: int) -> None:
         B, H, _, D = x.shape
@@ -237,23 +249,28 @@ class _TokenStore:
             raise RuntimeError("appended tensor does not match the cache: "
                                f"expected [B={self.codes.size(0)},H={self.codes.size(1)},n,D={self.D}] {self.scales.dtype}")
         cap = self.codes.size(2)
-        if need > cap:
+        if self.start + need <= cap:
+            return
+        # out of room at the tail: move the live tokens to the front of a buffer that is large enough
+        new_cap = cap if 2 * need <= cap else max(cap, 1 << (need - 1).bit_length())
+        if new_cap == cap and need > cap:
             new_cap = 1 << (need - 1).bit_length()
-            codes = torch.empty((B, H, new_cap, W), dtype=self.codes.dtype, device=x.device)
-            codes[:, :, : self.T].copy_(self.codes[:, :, : self.T])
-            scales = torch.empty(new_cap, dtype=self.scales.dtype, device=x.device)
-            scales[: self.T].copy_(self.scales[: self.T])
-            s32 = torch.empty(new_cap, dtype=torch.float32, device=x.device)
-            s32[: self.T].copy_(self.scales_f32[: self.T])
-            self.codes, self.scales, self.scales_f32 = codes, scales, s32
+        codes = torch.empty((B, H, new_cap, W), dtype=self.codes.dtype, device=x.device)
+        codes[:, :, : self.T].copy_(self.live_codes())
+        scales = torch.empty(new_cap, dtype=self.scales.dtype, device=x.device)
+        scales[: self.T].copy_(self.live_scales())
+        s32 = torch.empty(new_cap, dtype=torch.float32, device=x.device)
+        s32[: self.T].copy_(self.live_scales_f32())
+        self.codes, self.scales, self.scales_f32, self.start = codes, scales, s32, 0
 
     def append_per_token(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
         """n tokens, one scale each, in one launch (two + an allreduce when head-sharded)."""
         n = x.size(2)
         self._reserve(x, n)
-        dst = self.codes[:, :, self.T: self.T + n]
-        sc = self.scales[self.T: self.T + n]
-        s32 = self.scales_f32[self.T: self.T + n]
+        lo = self.start + self.T
+        dst = self.codes[:, :, lo: lo + n]
+        sc = self.scales[lo: lo + n]
+        s32 = self.scales_f32[lo: lo + n]
         sh, st = L.shape_stride(x)
         lib, dt, stream = L.lib(), L.dtype_code(x.dtype), L.stream_ptr(x.device)
         if group is None:
@@ -276,7 +293,8 @@ class _TokenStore:
         (ops.py:181-210 calls the per-tensor helper on whatever it is handed)."""
         n = x.size(2)
         self._reserve(x, n)
-        dst = self.codes[:, :, self.T: self.T + n]
+        lo = self.start + self.T
+        dst = self.codes[:, :, lo: lo + n]
         bits = _absmax_bits(x, L.PER_TENSOR, group)
         one = torch.empty(1, dtype=x.dtype, device=x.device)
         one32 = torch.empty(1, dtype=torch.float32, device=x.device)
@@ -285,21 +303,29 @@ class _TokenStore:
         L.check(fn(x.data_ptr(), L.dtype_code(x.dtype), sh, st, L.PER_TENSOR | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), float(eps),
                    dst.data_ptr(), L.stride3(dst), one.data_ptr(), one32.data_ptr(), L.stream_ptr(x.device)), "kvq_quant (block)")
         L.count_launch()
-        self.scales[self.T: self.T + n] = one
-        self.scales_f32[self.T: self.T + n] = one32
+        self.scales[lo: lo + n] = one
+        self.scales_f32[lo: lo + n] = one32
         self.T += n
         self.n_scale_entries += 1
 
     def dequantize(self, out_dtype: torch.dtype) -> torch.Tensor:
         B, H = self.codes.shape[:2]
         out = torch.empty((B, H, self.T, self.D), dtype=out_dtype, device=self.codes.device)
-        src = self.codes[:, :, : self.T]
+        src = self.live_codes()
+        scales = self.live_scales()
         sh = L.I64x4(B, H, self.T, self.D)
         fn = L.lib().kvq_dequant_int8 if self.bits == 8 else L.lib().kvq_dequant_int4_unpack
-        L.check(fn(src.data_ptr(), sh, L.stride3(src), self.scales.data_ptr(), L.dtype_code(self.scales.dtype), L.PER_TOKEN,
+        L.check(fn(src.data_ptr(), sh, L.stride3(src), scales.data_ptr(), L.dtype_code(scales.dtype), L.PER_TOKEN,
                    out.data_ptr(), L.dtype_code(out_dtype), L.stream_ptr(out.device)), "kvq_dequant (per token)")
         L.count_launch()
         return out
+
+    def keep_last(self, n: int) -> None:
+        """Sliding window on the store: drop all but the last n tokens by moving `start` (no data movement)."""
+        if n < self.T:
+            self.start += self.T - n
+            self.T = n
+            self.n_scale_entries = n
 
     def evict(self, plan, table, kept_idx: torch.Tensor) -> None:
         """Compact the store to the tokens kept by an eviction plan: codes through the same index-computing gather
@@ -307,19 +333,17 @@ class _TokenStore:
         equals quantizing the trimmed fp cache, bit for bit."""
         from ..cache.implementations import gather_tokens
         n = int(plan.n_total)
-        live = self.codes[:, :, : self.T]
-        new_codes = gather_tokens(live, plan, table)
+        new_codes = gather_tokens(self.live_codes(), plan, table)
         cap = max(256, 1 << max(n - 1, 0).bit_length())
         codes = torch.empty((new_codes.size(0), new_codes.size(1), cap, new_codes.size(3)), dtype=self.codes.dtype,
                             device=self.codes.device)
         codes[:, :, :n].copy_(new_codes)
         scales = torch.empty(cap, dtype=self.scales.dtype, device=self.scales.device)
         s32 = torch.empty(cap, dtype=torch.float32, device=self.scales.device)
-        scales[:n] = self.scales[: self.T].index_select(0, kept_idx)
-        s32[:n] = self.scales_f32[: self.T].index_select(0, kept_idx)
+        scales[:n] = self.live_scales().index_select(0, kept_idx)
+        s32[:n] = self.live_scales_f32().index_select(0, kept_idx)
         self.codes, self.scales, self.scales_f32 = codes, scales, s32
-        self.T = n
-        self.n_scale_entries = n
+        self.start, self.T, self.n_scale_entries = 0, n, n
 
     def nbytes(self) -> int:
         if self.codes is None:
@@ -328,10 +352,10 @@ class _TokenStore:
         return B * H * self.T * W * self.codes.element_size() + self.n_scale_entries * self.scales.element_size()
 
     def token_views(self) -> List[torch.Tensor]:
-        return [] if self.codes is None else [self.codes[:, :, t: t + 1] for t in range(self.T)]
+        return [] if self.codes is None else [self.codes[:, :, self.start + t: self.start + t + 1] for t in range(self.T)]
 
     def scale_views(self) -> List[torch.Tensor]:
-        return [] if self.scales is None else [self.scales[t] for t in range(self.T)]
+        return [] if self.scales is None else [self.scales[self.start + t] for t in range(self.T)]
 
 
 class QuantizedLayerKV:
@@ -436,6 +460,10 @@ class QuantizedLayerKV:
                           keep=keep_per_block, budget=old_budget)
         if plan.identity:
             return T
+        if strategy == "sliding_window":  # a view in the reference (:136-138); here: move the start of the live region
+            self._k.keep_last(int(plan.n_total))
+            self._v.keep_last(int(plan.n_total))
+            return self._k.T
         dev = self._k.codes.device
         with torch.cuda.device(dev):
             table = _old_table(plan, dev)
@@ -452,9 +480,8 @@ class QuantizedLayerKV:
         the fused dequant decode attention."""
         if self._k.T == 0:
             raise ValueError("Empty cache")
-        T = self._k.T
-        return (self._k.codes[:, :, :T], self._k.scales_f32[:T], self._k.bits,
-                self._v.codes[:, :, :T], self._v.scales_f32[:T], self._v.bits)
+        return (self._k.live_codes(), self._k.live_scales_f32(), self._k.bits,
+                self._v.live_codes(), self._v.live_scales_f32(), self._v.bits)
 
     def estimated_bytes(self) -> int:
         """Stored codes + scales, as the reference counts them (ops.py:271-290)."""

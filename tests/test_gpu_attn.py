@@ -108,3 +108,29 @@ def test_exact_current_token_merge(kvq, oracle):
         want = torch.matmul(w, vv).float()
         got = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb, k_cur=kcur.cuda(), v_cur=vcur.cuda())
         torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_attention_on_a_slid_store(kvq, oracle):
+    """After a zero-copy sliding window the live region starts at an arbitrary token offset (scales no longer 16-byte
+    aligned): the fused kernels must read exactly that region."""
+    B, H, T, D = 2, 4, 777, 128
+    g = torch.Generator().manual_seed(5)
+    k, v, q = torch.randn(B, H, T, D, generator=g), torch.randn(B, H, T, D, generator=g), torch.randn(B, H, 1, D, generator=g)
+    layer = kvq.QuantizedLayerKV("mixed", "cuda", torch.float32)
+    layer.append_tokens(k.cuda(), v.cuda())
+    for w in (701, 333, 130):
+        assert layer.evict("sliding_window", window_size=w) == w
+        kc, ks, kb, vc, vs, vb = layer.quantized()
+        assert kc.shape[2] == w
+        ok, oks, _ = oracle.quantize_per_token(k[:, :, T - w:].contiguous(), 8)
+        ov, ovs, _ = oracle.quantize_per_token(v[:, :, T - w:].contiguous(), 4)
+        assert torch.equal(kc.cpu(), ok) and torch.equal(vs.cpu(), ovs.float())
+        want = oracle.decode_attention(q, ok, 8, oks.float(), ov, 4, ovs.float())
+        got = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb)
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+    kd, _ = layer.get_kv()
+    assert kd.shape == (B, H, 130, D)
+    # appending past the end of the buffer compacts the live region and keeps its contents
+    before = layer.quantized()[0].clone()
+    layer.append_tokens(k[:, :, :400].cuda(), v[:, :, :400].cuda())
+    assert len(layer) == 530 and torch.equal(layer.quantized()[0][:, :, :130], before)
