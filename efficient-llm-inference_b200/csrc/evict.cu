@@ -394,15 +394,17 @@ extern "C" int kvq_paged_gather(const void* pool, int elem_bytes, const int64_t 
 // One token is B*H rows of D elements (<= a few tens of KB): a single element-wise kernel; the block
 // table lookup for the one logical block is done by the device (table stays resident on the GPU).
 namespace kvq { namespace {
+// n tokens starting at logical position t (n == 1: the reference's per-token append; n > 1: a whole prompt in one launch)
 template <typename E>
 __global__ void __launch_bounds__(kThreads) paged_append_tbl_kernel(const E* __restrict__ x, E* __restrict__ pool, int64_t B,
-                                                                   int64_t H, int64_t D, int64_t sB, int64_t sH, int64_t sD,
-                                                                   int64_t block, const int32_t* __restrict__ table, int64_t t) {
-    const int64_t lb = t / block, slot = t - lb * block, phys = table[lb];
-    const int64_t n = B * H * D;
+                                                                   int64_t H, int64_t N, int64_t D, int64_t sB, int64_t sH,
+                                                                   int64_t sT, int64_t sD, int64_t block,
+                                                                   const int32_t* __restrict__ table, int64_t t) {
+    const int64_t n = B * H * N * D;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-        const int64_t d = i % D, p = i / D, h = p % H, b = p / H;
-        pool[((phys * B * H + p) * block + slot) * D + d] = x[b * sB + h * sH + d * sD];
+        const int64_t d = i % D, r = i / D, j = r % N, p = r / N, h = p % H, b = p / H;
+        const int64_t lt = t + j, lb = lt / block, slot = lt - lb * block, phys = table[lb];
+        pool[((phys * B * H + p) * block + slot) * D + d] = x[b * sB + h * sH + j * sT + d * sD];
     }
 }
 } }
@@ -411,14 +413,14 @@ extern "C" int kvq_paged_append(const void* x, int elem_bytes, const int64_t sha
                                 const int32_t* block_table, int64_t block_size, int64_t t, kvq_stream_t stream) {
     KVQ_REQUIRE(x && pool && shape && stride && block_table, "null pointer");
     KVQ_REQUIRE(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4, "elem_bytes must be 1, 2 or 4");
-    KVQ_REQUIRE(shape[2] == 1, "paged append takes one token: shape[2] must be 1 (implementations.py:64-66)");
+    KVQ_REQUIRE(shape[2] >= 1, "paged append needs at least one token (shape[2] >= 1)");
     KVQ_REQUIRE(block_size >= 1 && t >= 0, "bad block_size / t");
-    const int64_t B = shape[0], H = shape[1], D = shape[3];
+    const int64_t B = shape[0], H = shape[1], N = shape[2], D = shape[3];
     if (B * H * D == 0) return KVQ_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = gen_grid(B * H * D);
-#define KVQ_PA(E) paged_append_tbl_kernel<E><<<grid, kThreads, 0, st>>>((const E*)x, (E*)pool, B, H, D, stride[0], stride[1], stride[3], \
-                                                                        block_size, block_table, t)
+    const unsigned grid = gen_grid(B * H * N * D);
+#define KVQ_PA(E) paged_append_tbl_kernel<E><<<grid, kThreads, 0, st>>>((const E*)x, (E*)pool, B, H, N, D, stride[0], stride[1], stride[2], \
+                                                                        stride[3], block_size, block_table, t)
     if (elem_bytes == 1) KVQ_PA(uint8_t); else if (elem_bytes == 2) KVQ_PA(uint16_t); else KVQ_PA(uint32_t);
 #undef KVQ_PA
     return check_launch("paged_append");

@@ -234,8 +234,7 @@ class KVCacheBenchmarker:
             if pages is None:
                 pages = state["p"] = [PagedKVCache(block_size=block_size, device=self.device, dtype=dtype) for _ in kv]
                 for cache, (k, v) in zip(pages, kv):
-                    for t in range(k.size(2)):
-                        cache.append(k[:, :, t:t + 1, :], v[:, :, t:t + 1, :])
+                    cache.append_tokens(k, v)  # the reference appends the prompt token by token (:528-530): same result
             else:
                 for cache, (k, v) in zip(pages, kv):
                     cache.append(k[:, :, -1:, :], v[:, :, -1:, :])

@@ -244,6 +244,31 @@ class PagedKVCache:
         self.t_filled += 1
 
     @torch.no_grad()
+    def append_tokens(self, k: torch.Tensor, v: torch.Tensor) -> None:
+        """Append n tokens [B,H,n,D] at once: same result as n append() calls (the reference's prompt loop,
+        benchmarker.py:528-530), one launch per tensor."""
+        assert k.dim() == 4 and v.dim() == 4
+        B, H, n, D = k.shape
+        if n == 0:
+            return
+        L.require_cuda(k, v)
+        if self._B is None:
+            self._B, self._H, self._D = B, H, D
+        while self.num_blocks() * self.block_size < self.t_filled + n:
+            self._alloc_block(B, H, D)
+        with L.device_guard(k):
+            stream = L.stream_ptr(k.device)
+            for x, pool in ((k, self._k_pool), (v, self._v_pool)):
+                if x.dtype != self.dtype:
+                    x = x.to(self.dtype)
+                sh, st = L.shape_stride(x)
+                L.check(L.lib().kvq_paged_append(x.data_ptr(), x.element_size(), sh, st, pool.data_ptr(),
+                                                 self._table.data_ptr(), self.block_size, self.t_filled, stream),
+                        "kvq_paged_append")
+                L.count_launch()
+        self.t_filled += n
+
+    @torch.no_grad()
     def get_kv(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Contiguous (K, V), each [B,H,T,D], stitched through the block table in one launch each."""
         if self.t_filled == 0:

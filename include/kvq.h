@@ -203,8 +203,9 @@ KVQ_API int kvq_evict_gather(const void* src, int elem_bytes, const int64_t shap
  * The reference keeps a Python list of [B,H,block,D] tensors whose list index is the logical block
  * (implementations.py:36-54). */
 
-/* Writes one token (x is [B,H,1,D], strided) into slot t % block_size of logical block t / block_size.
- * Replaces: PagedKVCache.append implementations.py:57-80. */
+/* Writes the n = shape[2] tokens of x ([B,H,n,D], strided) at logical positions t .. t+n-1: token t+j goes to slot
+ * (t+j) % block_size of logical block (t+j) / block_size (every block touched must be in the table).  n = 1 is
+ * PagedKVCache.append (implementations.py:57-80); n > 1 replaces the per-token prompt loop benchmarker.py:528-530. */
 KVQ_API int kvq_paged_append(const void* x, int elem_bytes, const int64_t shape[4], const int64_t stride[4], void* pool,
                      const int32_t* block_table, int64_t block_size, int64_t t, kvq_stream_t stream);
 

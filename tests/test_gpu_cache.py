@@ -212,3 +212,17 @@ def test_evict_on_quantized_store_equals_quantizing_the_evicted_cache(kvq, oracl
         assert torch.equal(ks.cpu(), oks.float()) and torch.equal(vs.cpu(), ovs.float()), strat
         layer.append_tokens(x[:, :, :3].cuda(), y[:, :, :3].cuda())  # the store keeps working after compaction
         assert len(layer) == n + 3 and layer.estimated_bytes() > 0
+
+
+def test_paged_bulk_append_equals_token_by_token(kvq):
+    k, v = gen((2, 3, 150, 64), torch.float16, 8).cuda(), gen((2, 3, 150, 64), torch.float16, 9).cuda()
+    hf = k.transpose(1, 2).contiguous().transpose(1, 2)
+    a, b = kvq.PagedKVCache(16, "cuda", torch.float16), kvq.PagedKVCache(16, "cuda", torch.float16)
+    a.append_tokens(hf[:, :, :70], v[:, :, :70])
+    a.append(hf[:, :, 70:71], v[:, :, 70:71])
+    a.append_tokens(hf[:, :, 71:], v[:, :, 71:])
+    for t in range(150):
+        b.append(hf[:, :, t:t + 1], v[:, :, t:t + 1])
+    (ka, va), (kb, vb) = a.get_kv(), b.get_kv()
+    assert torch.equal(ka, k) and torch.equal(va, v) and torch.equal(kb, k) and torch.equal(vb, v)
+    assert (a.num_blocks(), a.allocated_bytes(), a.used_bytes(), a.t_filled) == (b.num_blocks(), b.allocated_bytes(), b.used_bytes(), b.t_filled)
