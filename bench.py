@@ -298,6 +298,7 @@ def run_c3(args, cfg):
 
     del xs, packed, outs, x0, x, tx, tp, to  # the e2e leg brings its data from the host
     torch.cuda.empty_cache()
+    decode = run_decode(args, dev, rank, world) if not args.skip_decode else None
     e2e = run_e2e(args, cfg, dev, Hl, world) if not args.skip_e2e else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0,
                                                                           "d2h_bytes_per_step": 0, "_ms": 1.0, "_job_bytes": 0.0}
     cpu = None
@@ -325,12 +326,79 @@ def run_c3(args, cfg):
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms, "launches_timed": len(dom_events),
                          "traffic": (lambda t: None if t is None else t * n_tensors * n_local / (16 * 8 * 32768 * 128))(ncu_traffic("dequant_flat_int4_bf16"))},
             "cpu_baseline": cpu,
+            "decode": decode,
             "sm_count": sm.value,
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+C5 = dict(L=80, B=8, H=8, T=65536, D=128)  # Llama-3-70B-shape KV (BASELINE.json configs[4]), INT8-K / INT4-V
+
+
+def run_decode(args, dev, rank, world):
+    """Second half of the metric ("decode tok/s"): fused dequant decode attention over the C5 cache, head-sharded (no
+    collective: heads are independent).  One step = the attention of all 80 layers for a batch of 8 sequences at 64k
+    context; tok/s = B / step time (max over ranks).  Captured in a CUDA graph so the GPU time is not hidden behind
+    Python; reported for the MHA shape (one query head per KV head: bandwidth-bound) and for Llama-3-70B's real GQA
+    (8 query heads per KV head: FMA-bound on CUDA cores)."""
+    import torch
+    import torch.distributed as dist
+
+    import kvq_b200
+    from kvq_b200.distributed import head_shard_range
+
+    c = C5
+    lo, hi = head_shard_range(c["H"], rank, world)
+    Hl, B, T, D, Lyr = hi - lo, c["B"], c["T"], c["D"], c["L"]
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    kcs = [torch.randint(-127, 128, (B, Hl, T, D), device=dev, dtype=torch.int8, generator=g) for _ in range(Lyr)]
+    vcs = [torch.randint(0, 256, (B, Hl, T, D // 2), device=dev, dtype=torch.uint8, generator=g) for _ in range(Lyr)]
+    ksc = torch.rand(T, device=dev, generator=g) * 0.01 + 0.01
+    vsc = torch.rand(T, device=dev, generator=g) * 0.01 + 0.01
+    ws = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    out = {}
+    nbytes = Lyr * (B * Hl * T * (D + D // 2) + 8 * T)
+    for name, G in (("mha", 1), ("gqa8", 8)):
+        q = torch.randn(B, Hl * G, 1, D, device=dev, dtype=torch.bfloat16, generator=g)
+
+        def step():
+            for l in range(Lyr):
+                kvq_b200.decode_attention_quantized(q, kcs[l], ksc, 8, vcs[l], vsc, 4, workspace=ws)
+
+        step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(3):
+            graph.replay()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        out[name] = {"tok_s": B / (ms * 1e-3), "ms_per_step": ms, "gbs_whole_job": nbytes * world / (ms * 1e-3) / 1e9,
+                     "q_heads_per_kv_head": G}
+        del graph
+    out["config"] = (f"Llama-3-70B-shape synthetic KV (L={Lyr}, {c['H']} KV heads, D={D}) batch {B} x {T} context, INT8-K / INT4-V "
+                     f"per-token-scaled cache, fused dequant decode attention, head-sharded over {world} GPU(s); BASELINE.json configs[4]")
+    out["launches_per_step"] = 2 * Lyr
+    del kcs, vcs
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(args, cfg, dev, Hl, world):
@@ -430,6 +498,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="override the number of layers (debug only; not a valid bench line)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline leg")
+    ap.add_argument("--skip-decode", action="store_true", help="profiling runs only: leave out the decode-attention (C5) leg")
     args = ap.parse_args()
     cfg = dict(C3)
     if args.layers:
