@@ -16,6 +16,9 @@
 // r = fma(-q0,scale,x); q1 = fma(r,y,q0), which gives the same code as rint(x/scale) for EVERY
 // fp16/bf16 x and every possible scale (proved by exhaustion: oracle kvqo_check_division_free,
 // tests/test_exact_division.py).  fp32 inputs use the IEEE division (__fdiv_rn).
+#include <cstdio>
+#include <cstdlib>
+
 #include "kvq_common.cuh"
 
 namespace kvq {
@@ -119,73 +122,81 @@ template <int DT, int BITS> struct OutBytes { static constexpr int value = InVec
 
 // ---- flat kernels: contiguous input and output, per-tensor scale ---------------------------------------------
 
-// Chunk c of tensor ti (a chunk = kThreads * unroll vectors) belongs to CTA (ti * chunks_per_tensor + c) % gridDim.x: the
-// left-over chunks of every tensor start where the previous tensor stopped, so CTAs stay balanced to within one chunk
-// over the whole launch (with a fixed start, the same CTAs would take the extra chunk of all 64 tensors).
-__device__ __forceinline__ int64_t first_chunk(int ti, int64_t n_vec, int unroll) {
-    if (ti == 0) return blockIdx.x;
-    const int64_t per = (int64_t)kThreads * unroll, chunks = (n_vec + per - 1) / per;
-    const int64_t shift = ((int64_t)ti * chunks) % gridDim.x;
-    return ((int64_t)blockIdx.x + gridDim.x - shift) % gridDim.x;
+// Flat kernels: NOT persistent.  A chunk is kThreads * UNROLL consecutive vectors (16-32 KB); CTA b owns `cpc` consecutive
+// chunks of one tensor, and the hardware hands CTAs out in index order, so the set of resident CTAs sweeps memory as one
+// contiguous window.  On B200 this beats a grid-stride loop over 148 x k resident CTAs by up to 19 % on the write-heavy
+// dequantize stream (5.5 -> 6.6 TB/s) and 5-8 % on the read-heavy ones (profiles/r1c_grid_sweep.log).
+// Batched form (xs != nullptr): the grid covers n_tensors x blocks_per_tensor CTAs, tensor-major, so the sweep runs through
+// one tensor after the other exactly like separate launches would, without the launch gaps.  Entry i of absmax_bits /
+// scale_out / scale_f32_out belongs to tensor i.
+struct FlatWork {
+    int64_t chunks;   // chunks per tensor
+    int bpt;          // CTAs (blocks) per tensor
+    int cpc;          // chunks per CTA
+    int cstep;        // distance between a CTA's chunks: 1 = consecutive chunks, bpt = strided over the tensor
+};
+// CTA -> tensor index and its chunks c0, c0 + cstep, ... (< c1)
+__device__ __forceinline__ void flat_split(const FlatWork& w, int& ti, int64_t& c0, int64_t& c1) {
+    ti = blockIdx.x / w.bpt;
+    const int b = blockIdx.x - ti * w.bpt;
+    if (w.cstep == 1) { c0 = (int64_t)b * w.cpc; c1 = c0 + w.cpc < w.chunks ? c0 + w.cpc : w.chunks; }
+    else { c0 = b; c1 = w.chunks; }
 }
 
-// Batched form (xs != nullptr): n_tensors tensors of n_vec vectors each, walked IN ORDER by every CTA (grid-stride inside
-// each tensor), so the whole grid streams through one tensor at a time exactly like n separate launches would, without the
-// launch gaps.  Entry i of absmax_bits / scale_out / scale_f32_out belongs to tensor i.
 template <int DT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
-                                                               uint32_t* __restrict__ absmax_bits,
-                                                               const void* const* __restrict__ xs = nullptr, int n_tensors = 1) {
+                                                               uint32_t* __restrict__ absmax_bits, FlatWork w,
+                                                               const void* const* __restrict__ xs = nullptr) {
     __shared__ uint32_t red[kThreads / 32];
-    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int ti = 0; ti < n_tensors; ++ti) {
-        const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
-        uint32_t m = 0;
-        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-            uint4 v[UNROLL];
+    int ti; int64_t c0, c1;
+    flat_split(w, ti, c0, c1);
+    const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
+    uint32_t m = 0;
+    for (int64_t c = c0; c < c1; c += w.cstep) {
+        const int64_t i = c * (kThreads * UNROLL) + threadIdx.x;
+        uint4 v[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t j = i + (int64_t)u * kThreads;
-                v[u] = j < n_vec ? ld_stream(xt + j) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            v[u] = j < n_vec ? ld_stream(xt + j) : make_uint4(0, 0, 0, 0);
         }
-        m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
-        if (threadIdx.x == 0 && m != 0) atomicMax(absmax_bits + ti, m);
-        __syncthreads();  // `red` is reused by the next tensor
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[u]));
     }
+    m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+    // thousands of CTAs per tensor: only those that can still raise the max touch the atomic
+    if (threadIdx.x == 0 && m > *reinterpret_cast<volatile uint32_t*>(absmax_bits + ti)) atomicMax(absmax_bits + ti, m);
 }
 
 template <int DT, int BITS, int UNROLL, bool CLAMP>
 __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
                                                               const uint32_t* __restrict__ absmax_bits, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
-                                                              float* __restrict__ scale_f32_out,
+                                                              float* __restrict__ scale_f32_out, FlatWork w,
                                                               const void* const* __restrict__ xs = nullptr,
-                                                              void* const* __restrict__ qs = nullptr, int n_tensors = 1) {
+                                                              void* const* __restrict__ qs = nullptr) {
     constexpr int kOut = OutBytes<DT, BITS>::value;
-    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int ti = 0; ti < n_tensors; ++ti) {
-        const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
-        char* qt = xs ? reinterpret_cast<char*>(qs[ti]) : q;
-        const Scale sc = scale_from_bits<BITS>(absmax_bits[ti], eps);
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            if (scale_out) store_scalar<DT>(scale_out, ti, sc.s);
-            if (scale_f32_out) scale_f32_out[ti] = round_through<DT>(sc.s);
+    int ti; int64_t c0, c1;
+    flat_split(w, ti, c0, c1);
+    const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
+    char* qt = xs ? reinterpret_cast<char*>(qs[ti]) : q;
+    const Scale sc = scale_from_bits<BITS>(absmax_bits[ti], eps);
+    if (c0 == 0 && threadIdx.x == 0) {
+        if (scale_out) store_scalar<DT>(scale_out, ti, sc.s);
+        if (scale_f32_out) scale_f32_out[ti] = round_through<DT>(sc.s);
+    }
+    for (int64_t c = c0; c < c1; c += w.cstep) {
+        const int64_t i = c * (kThreads * UNROLL) + threadIdx.x;
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) v[u] = ld_stream(xt + j);
         }
-        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-            uint4 v[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t j = i + (int64_t)u * kThreads;
-                if (j < n_vec) v[u] = ld_stream(xt + j);
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t j = i + (int64_t)u * kThreads;
-                if (j < n_vec) quant_store<DT, BITS, CLAMP>(v[u], sc, qt + j * kOut);
-            }
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) quant_store<DT, BITS, CLAMP>(v[u], sc, qt + j * kOut);
         }
     }
 }
@@ -549,28 +560,28 @@ __device__ __forceinline__ void dequant_store(const Raw<CodeIn<ODT, BITS>::kByte
 template <int ODT, int BITS, bool PK, int UNROLL>
 __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __restrict__ codes, int64_t n_vec,
                                                                 const void* __restrict__ scale, int scale_dtype,
-                                                                uint4* __restrict__ out,
+                                                                uint4* __restrict__ out, FlatWork w,
                                                                 const void* const* __restrict__ cs = nullptr,
-                                                                void* const* __restrict__ os = nullptr, int n_tensors = 1) {
+                                                                void* const* __restrict__ os = nullptr) {
     constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
-    const int64_t step = (int64_t)gridDim.x * kThreads * UNROLL;
-    for (int ti = 0; ti < n_tensors; ++ti) {  // batched form: tensors in order, one scale each (see absmax_flat_kernel)
-        const char* ct = cs ? reinterpret_cast<const char*>(cs[ti]) : codes;
-        uint4* ot = cs ? reinterpret_cast<uint4*>(os[ti]) : out;
-        ScaleArg<PK> sa;
-        sa.load(scale, scale_dtype, ti);
-        for (int64_t i = first_chunk(ti, n_vec, UNROLL) * kThreads * UNROLL + threadIdx.x; i < n_vec; i += step) {
-            Raw<kIn> r[UNROLL];
+    int ti; int64_t c0, c1;
+    flat_split(w, ti, c0, c1);  // batched form: tensor-major grid, one scale per tensor (see absmax_flat_kernel)
+    const char* ct = cs ? reinterpret_cast<const char*>(cs[ti]) : codes;
+    uint4* ot = cs ? reinterpret_cast<uint4*>(os[ti]) : out;
+    ScaleArg<PK> sa;
+    sa.load(scale, scale_dtype, ti);
+    for (int64_t c = c0; c < c1; c += w.cstep) {
+        const int64_t i = c * (kThreads * UNROLL) + threadIdx.x;
+        Raw<kIn> r[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t j = i + (int64_t)u * kThreads;
-                if (j < n_vec) r[u].load(ct + j * kIn);
-            }
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) r[u].load(ct + j * kIn);
+        }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t j = i + (int64_t)u * kThreads;
-                if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sa, ot + j);
-            }
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = i + (int64_t)u * kThreads;
+            if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sa, ot + j);
         }
     }
 }
@@ -654,11 +665,19 @@ RowGeom row_geom(const View4& v, int es, const Stride3& q, int qes, int vpr) {
     return g;
 }
 
+// grid sizes of the strided-row and per-token kernels, in CTAs per SM (KVQ_ROWS_CTAS_PER_SM / KVQ_TOKEN_CTAS_PER_SM: tuning knobs)
+int env_int(const char* name, int dflt) { const char* e = getenv(name); const int n = e ? atoi(e) : 0; return n > 0 ? n : dflt; }
+// measured on B200 (profiles/r1c_grid_sweep.log): many short CTAs beat a few persistent ones here too; the quantize rows
+// kernel (two block barriers per tile) peaks at 32 per SM, the barrier-free dequantize / absmax rows kernels at 128
+int quant_rows_ctas_per_sm() { static const int v = env_int("KVQ_QROWS_CTAS_PER_SM", 32); return v; }
+int rows_ctas_per_sm() { static const int v = env_int("KVQ_ROWS_CTAS_PER_SM", 128); return v; }
+int token_ctas_per_sm() { static const int v = env_int("KVQ_TOKEN_CTAS_PER_SM", 32); return v; }
+
 // planes are looped inside the CTA (the per-tile scales are reused): y covers at most 8 plane groups
 dim3 row_grid_planes_inside(const RowGeom& g, int unroll) {
     const int rpp = kThreads / g.vpr;
     const int64_t tiles = (g.T + (int64_t)rpp * unroll - 1) / ((int64_t)rpp * unroll);
-    const int64_t total = (int64_t)sm_count() * 16;
+    const int64_t total = (int64_t)sm_count() * quant_rows_ctas_per_sm();
     int64_t gx = tiles < total ? tiles : total;
     int64_t gy = (total + gx - 1) / gx;
     if (gy > g.nP) gy = g.nP;
@@ -670,14 +689,48 @@ dim3 row_grid(const RowGeom& g, int unroll) {
     const int rpp = kThreads / g.vpr;
     const int64_t tiles = (g.T + (int64_t)rpp * unroll - 1) / ((int64_t)rpp * unroll);
     const unsigned gy = (unsigned)(g.nP < 65535 ? g.nP : 65535);
-    const int64_t want = ((int64_t)sm_count() * 16 + gy - 1) / gy;  // ~16 CTAs per SM in total
+    const int64_t want = ((int64_t)sm_count() * rows_ctas_per_sm() + gy - 1) / gy;
     const int64_t gx = tiles < want ? tiles : want;
     return dim3((unsigned)(gx > 0 ? gx : 1), gy, 1);
 }
-unsigned flat_grid(int64_t n_vec, int unroll) {
-    const int64_t blocks = (n_vec + (int64_t)kThreads * unroll - 1) / ((int64_t)kThreads * unroll);
-    const int64_t cap = (int64_t)sm_count() * 16;
-    return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+// Work split of the flat kernels per kernel kind (0 absmax, 1 quantize, 2 dequantize).  v > 0: v consecutive chunks per CTA;
+// v < 0: |v| CTAs per SM per tensor, each striding over the tensor.  KVQ_FLAT_MODE="a,q,d" overrides (tuning knob).
+// Measured on B200 with 1 GiB bf16 tensors (profiles/r1c_grid_sweep.log): the write-heavy dequantize stream wants one
+// 16 KB chunk per CTA (6.6 TB/s vs 5.5 with 16 persistent CTAs per SM), the issue-bound quantize and the read-only absmax
+// want ~128 short CTAs per SM.
+int flat_mode(int kind) {
+    static int v[3] = {0, 0, 0};
+    static const bool init = [] {
+        v[0] = -128; v[1] = -128; v[2] = 1;
+        if (const char* e = getenv("KVQ_FLAT_MODE")) { int a = 0, q = 0, d = 0; if (sscanf(e, "%d,%d,%d", &a, &q, &d) == 3 && a && q && d) { v[0] = a; v[1] = q; v[2] = d; } }
+        return true;
+    }();
+    (void)init;
+    return v[kind];
+}
+void flat_work(int64_t n_vec, int unroll, int kind, int64_t n_tensors, FlatWork& w, unsigned& grid) {
+    const int64_t per = (int64_t)kThreads * unroll;
+    w.chunks = (n_vec + per - 1) / per;
+    const int mode = flat_mode(kind);
+    const int64_t max_bpt = 0x7fffffffLL / (n_tensors > 0 ? n_tensors : 1);
+    int64_t bpt, cpc;
+    if (mode < 0) {
+        bpt = (int64_t)sm_count() * -mode;
+        if (bpt > w.chunks) bpt = w.chunks;
+        if (bpt > max_bpt) bpt = max_bpt;
+        if (bpt < 1) bpt = 1;
+        cpc = (w.chunks + bpt - 1) / bpt;
+        w.cstep = (int)bpt;
+    } else {
+        cpc = mode;
+        bpt = (w.chunks + cpc - 1) / cpc;
+        while (bpt > max_bpt) { cpc *= 2; bpt = (w.chunks + cpc - 1) / cpc; }
+        if (bpt < 1) bpt = 1;
+        w.cstep = 1;
+    }
+    w.bpt = (int)bpt; w.cpc = (int)cpc;
+    if (w.cstep != 1 && bpt == 1) w.cstep = 1, w.cpc = (int)w.chunks;  // a single CTA walks consecutive chunks
+    grid = (unsigned)(bpt * n_tensors);
 }
 
 GenGeom gen_geom(const View4& v, const Stride3& q) {
@@ -720,12 +773,14 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
         codes_ok(q, qs, piece)) {
         const int64_t n_vec = n * es / 16;
         constexpr int U = 4;
+        FlatWork w; unsigned grid;
+        flat_work(n_vec, U, 1, 1, w, grid);
         if (covers) {
-            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, false><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
-                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, false><<<grid, kThreads, 0, st>>>(
+                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out, w));
         } else {
-            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, true><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
-                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out));
+            KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, true><<<grid, kThreads, 0, st>>>(
+                                       (const uint4*)x, n_vec, absmax_bits, eps, (char*)q, scale_out, scale_f32_out, w));
         }
     } else if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece)) {
         const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
@@ -768,12 +823,14 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
     if (!per_token && c_contig && rows_ok) {
         const int64_t n_vec = n * oes / 16;
         constexpr int U = 4;
+        FlatWork w; unsigned grid;
+        flat_work(n_vec, U, 2, 1, w, grid);
         if (pk) {
-            if (out_dtype == KVQ_F16) dequant_flat_kernel<KVQ_F16, BITS, true, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out);
-            else dequant_flat_kernel<KVQ_BF16, BITS, true, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out);
+            if (out_dtype == KVQ_F16) dequant_flat_kernel<KVQ_F16, BITS, true, U><<<grid, kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w);
+            else dequant_flat_kernel<KVQ_BF16, BITS, true, U><<<grid, kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w);
         } else {
-            KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, false, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>(
-                                           (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out));
+            KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, false, U><<<grid, kThreads, 0, st>>>(
+                                           (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w));
         }
     } else if (rows_ok) {
         const int64_t contig[4] = {H * T * D, T * D, D, 1};
@@ -809,7 +866,7 @@ void launch_token_fused(int nv, unsigned grid, cudaStream_t st, const void* x, c
 }
 
 unsigned token_grid(int64_t T) {
-    const int64_t cap = (int64_t)sm_count() * 8;
+    const int64_t cap = (int64_t)sm_count() * token_ctas_per_sm();
     return (unsigned)(T < cap ? T : cap);
 }
 
@@ -845,7 +902,9 @@ extern "C" int kvq_absmax(const void* x, int dtype, const int64_t shape[4], cons
     } else if (is_contiguous(v) && aligned16(x) && (n * es) % 16 == 0 && !per_token) {
         const int64_t n_vec = n * es / 16;
         constexpr int U = 8;
-        KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<flat_grid(n_vec, U), kThreads, 0, st>>>((const uint4*)x, n_vec, absmax_bits));
+        FlatWork w; unsigned grid;
+        flat_work(n_vec, U, 0, 1, w, grid);
+        KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<grid, kThreads, 0, st>>>((const uint4*)x, n_vec, absmax_bits, w));
     } else if (fast) {
         const RowGeom g = row_geom(v, es, Stride3{0, 0, 0}, 1, (int)(v.D * es / 16));
         constexpr int U = 8;
@@ -928,9 +987,6 @@ extern "C" int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shap
 // One launch per phase for a whole step (all layers x {K,V}) instead of one per tensor: at 1/8 of a cache per GPU the
 // per-tensor kernels last 20-30 us and launch gaps dominate.  Pointer tables live on the device.
 
-namespace kvq { namespace {
-unsigned batched_grid(int64_t n_vec, int unroll, int64_t) { return flat_grid(n_vec, unroll); }
-} }
 
 extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
                                   kvq_stream_t stream) {
@@ -945,7 +1001,9 @@ extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_te
     KVQ_REQUIRE((numel * es) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
     const int64_t n_vec = numel * es / 16;
     constexpr int U = 8;
-    KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>(nullptr, n_vec, absmax_bits, xs, (int)n_tensors));
+    FlatWork w; unsigned grid;
+    flat_work(n_vec, U, 0, n_tensors, w, grid);
+    KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, absmax_bits, w, xs));
     return check_launch("absmax_batched");
 }
 
@@ -964,8 +1022,10 @@ extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_ten
     KVQ_REQUIRE((numel * es) % 16 == 0, "batched kernels need numel * elem_size to be a multiple of 16");
     const int64_t n_vec = numel * es / 16;
     constexpr int U = 4;
-#define KVQ_QB(BITS, CL) KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, CL><<<batched_grid(n_vec, U, n_tensors), kThreads, 0, st>>>( \
-                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, xs, qs, (int)n_tensors))
+    FlatWork w; unsigned grid;
+    flat_work(n_vec, U, 1, n_tensors, w, grid);
+#define KVQ_QB(BITS, CL) KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, CL><<<grid, kThreads, 0, st>>>( \
+                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, w, xs, qs))
     if (bits == 8) { if (covers) { KVQ_QB(8, false); } else { KVQ_QB(8, true); } }
     else { if (covers) { KVQ_QB(4, false); } else { KVQ_QB(4, true); } }
 #undef KVQ_QB
@@ -985,8 +1045,9 @@ extern "C" int kvq_dequant_batched(const void* const* codes, int bits, int64_t n
     const int64_t n_vec = numel * oes / 16;
     const bool pk = scale_dtype == out_dtype && out_dtype != KVQ_F32;
     constexpr int U = 4;
-    const unsigned grid = batched_grid(n_vec, U, n_tensors);
-#define KVQ_DQB(ODT, BITS, PK) dequant_flat_kernel<ODT, BITS, PK, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, scales, scale_dtype, nullptr, codes, outs, (int)n_tensors)
+    FlatWork w; unsigned grid;
+    flat_work(n_vec, U, 2, n_tensors, w, grid);
+#define KVQ_DQB(ODT, BITS, PK) dequant_flat_kernel<ODT, BITS, PK, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, scales, scale_dtype, nullptr, w, codes, outs)
     if (bits == 8) {
         if (pk) { if (out_dtype == KVQ_F16) KVQ_DQB(KVQ_F16, 8, true); else KVQ_DQB(KVQ_BF16, 8, true); }
         else { KVQ_DISPATCH_DT(out_dtype, KVQ_DQB(DT, 8, false)); }
