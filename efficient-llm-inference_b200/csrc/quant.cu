@@ -8,9 +8,10 @@
 //
 // Everything here is HBM-bound streaming work.  The unit of work is one 16-byte vector per lane, so
 // every warp-level load and store covers one contiguous, fully used run of sectors; a thread keeps
-// several vectors in flight, and all kernels are grid-stride loops so that per-thread setup is
-// amortised (the first version spent half its issue slots on address arithmetic).  The max is reduced
-// with REDUX per warp and one atomicMax per CTA.
+// several vectors in flight and per-thread setup is hoisted out of the inner loop (the first version
+// spent half its issue slots on address arithmetic).  Launch shape: many short CTAs, not a few persistent
+// ones -- measured faster on B200 by 5-19 % (profiles/r1c_grid_sweep.log).  The max is reduced with REDUX
+// per warp and at most one atomicMax per CTA.
 //
 // The per-element division is replaced, for 16-bit inputs, by y = RN(1/scale); q0 = RN(x*y);
 // r = fma(-q0,scale,x); q1 = fma(r,y,q0), which gives the same code as rint(x/scale) for EVERY
@@ -122,9 +123,9 @@ template <int DT, int BITS> struct OutBytes { static constexpr int value = InVec
 
 // ---- flat kernels: contiguous input and output, per-tensor scale ---------------------------------------------
 
-// Flat kernels: NOT persistent.  A chunk is kThreads * UNROLL consecutive vectors (16-32 KB); CTA b owns `cpc` consecutive
-// chunks of one tensor, and the hardware hands CTAs out in index order, so the set of resident CTAs sweeps memory as one
-// contiguous window.  On B200 this beats a grid-stride loop over 148 x k resident CTAs by up to 19 % on the write-heavy
+// Flat kernels: NOT persistent.  A chunk is kThreads * UNROLL consecutive vectors (16-32 KB); a CTA owns a few chunks of one
+// tensor (consecutive, or strided over the tensor: FlatWork), and the hardware hands CTAs out in index order, so the set of
+// resident CTAs sweeps memory front to back.  On B200 this beats a grid-stride loop over 148 x k resident CTAs by up to 19 % on the write-heavy
 // dequantize stream (5.5 -> 6.6 TB/s) and 5-8 % on the read-heavy ones (profiles/r1c_grid_sweep.log).
 // Batched form (xs != nullptr): the grid covers n_tensors x blocks_per_tensor CTAs, tensor-major, so the sweep runs through
 // one tensor after the other exactly like separate launches would, without the launch gaps.  Entry i of absmax_bits /
