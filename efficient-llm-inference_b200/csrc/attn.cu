@@ -815,6 +815,326 @@ __global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams 
     }
 }
 
+// =====================================================================================================
+// Register-tiled variant for GQA groups (G = 4, 8: Llama-3-70B's 64 query heads on 8 KV heads is the C5 shape).
+// Every K/V element now feeds G query heads, so per KV head the step is a small [T x D] . [D x G] product
+// followed by [G x T] . [T x D]: on CUDA cores that is FFMA-bound, not HBM-bound (G FFMA per code against one
+// byte or nibble of traffic), and what matters is instructions per FFMA and keeping the FMA pipe fed.  The
+// G <= 2 kernels above spend ~10 instructions per (code, head); this one is laid out like a register-blocked
+// SGEMM, and every WARP runs its own online softmax over its own 16 tokens of each 128-token tile, so the main
+// loop has no block-wide barrier at all (the first tiled version had three per tile: 27 % of its stall samples):
+//   K phase : a lane owns 16 channels of RT tokens and accumulates a [RT tokens x G heads] block; a code is
+//             converted to fp32 once and used G times, a float4 of q (LDS.128, conflict-free padded layout)
+//             is used for RT tokens.  The D/16 lanes of a row are combined by a reduce-SCATTER: lane kc keeps
+//             its accumulators in the order head = j ^ swz(kc), so every halving step exchanges statically
+//             indexed registers (no selects) and lane kc ends with the full score of head kc.
+//   softmax : in the registers that hold the scores: warp max per head by shuffles, exp2 once per (token, head)
+//             -- the G <= 2 kernels recompute it in every V lane --, weights p * v_scale[t] to the warp's own
+//             [16][G] patch of shared memory (__syncwarp only).
+//   V phase : a lane owns 4 channels, the warp covers D; [G heads x 4 channels] accumulators per lane, weights
+//             read back as LDS.128 broadcasts.
+// Ring: cp.async.bulk + a `full` mbarrier per stage as in the other variants, plus an `empty` mbarrier per
+// stage (one arrival per warp) so that the producer thread only ever waits for the tile before last.
+// The eight per-warp partial results are merged through shared memory once per CTA; split / merge protocol
+// with the second kernel unchanged.
+// =====================================================================================================
+
+#ifndef KVQ_ATTN_GQA_STAGES
+#define KVQ_ATTN_GQA_STAGES 3
+#endif
+#ifndef KVQ_ATTN_GQA_CTAS_PER_SM
+#define KVQ_ATTN_GQA_CTAS_PER_SM 2
+#endif
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KBITS, int VBITS, int G, int D> struct GqaCfg {
+    static constexpr int NT = kThreads2, kWarps = NT / 32, WR = kTile / kWarps;  // WR = 16 tokens per warp per tile
+    static constexpr int kKRow = D * KBITS / 8, kVRow = D * VBITS / 8;
+    static constexpr int kKTile = kTile * kKRow, kVTile = kTile * kVRow, kStage = kKTile + kVTile;
+    static constexpr int kStages = KVQ_ATTN_GQA_STAGES;
+    static constexpr int LPR = D / 16;                          // K: lanes per token row, 16 channels each
+    static constexpr int QCH = 20;                              // floats per 16-channel chunk of q (4 pad: conflict-free LDS.128)
+    static constexpr int QP = ((LPR * QCH + 31) / 32) * 32;     // q row pitch (floats)
+    static constexpr int LPRV = D / 4, VRW = 32 / LPRV;         // V: lanes per token row (4 channels each), rows per warp pass
+    static constexpr int kRed = kWarps * VRW * G * D * 4;       // final merge of the warps' partials aliases the ring
+    static constexpr int kBuf = kStages * kStage > kRed ? kStages * kStage : kRed;
+    // q_s, per-warp weight patches, per-warp alpha / m / l, barriers
+    static constexpr int kSmem = kBuf + G * QP * 4 + kWarps * WR * G * 4 + 3 * kWarps * G * 4 + 2 * kStages * 8 + 16;
+};
+
+// 4 consecutive codes -> 4 floats.  INT8: word e4 of the lane's words; INT4: half (e4 & 1) of word e4 >> 1
+template <int BITS> __device__ __forceinline__ void cvt4(const uint32_t* w, int e4, float f[4]) {
+    if constexpr (BITS == 8) {
+        int8x4_to_float(w[e4], f);
+    } else {
+        const uint32_t x = w[e4 >> 1] >> (16 * (e4 & 1));
+        const uint32_t hi = (x >> 4) & 0x0f0fu, lo = x & 0x0f0fu;
+        f[0] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650)) - 8388616.f;
+        f[1] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650)) - 8388616.f;
+        f[2] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7651)) - 8388616.f;
+        f[3] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7651)) - 8388616.f;
+    }
+}
+
+template <int KBITS, int VBITS, int G, int D>
+__global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_attn_gqa_kernel(AttnParams P) {
+    using C = GqaCfg<KBITS, VBITS, G, D>;
+    constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR, QP = C::QP;
+    constexpr int LPR = C::LPR, RPP = 32 / LPR, RT = WR / RPP;  // K: rows per warp pass; register tile RT tokens x G heads
+    constexpr int KW = 16 * KBITS / 32;                         // code words per lane per token
+    constexpr int LPRV = C::LPRV, VRW = C::VRW, VP = WR / VRW;
+    constexpr int NREM = G > LPR ? G / LPR : 1;                 // scores a lane holds per token after the reduce-scatter
+    constexpr int S = C::kStages, PD = S > 2 ? S - 2 : 1;       // tiles in flight ahead of the math
+    static_assert(G == 4 || G == 8, "G");
+    static_assert(RT >= 1 && RT * RPP == WR, "tiling");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);  // [G][QP], chunks of 16 channels padded to 20 floats
+    float* p_s = q_s + G * QP;                                  // [kWarps][WR][G] weights p * v_scale
+    float* alpha_s = p_s + kWarps * WR * G;                     // [kWarps][G]
+    float* m_s = alpha_s + kWarps * G;                          // [kWarps][G]  (end of kernel)
+    float* l_s = m_s + kWarps * G;                              // [kWarps][G]  (end of kernel)
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(l_s + kWarps * G) + 7) & ~uintptr_t(7));
+    uint64_t* empty = full + S;
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t_begin = split * P.tokens_per_split;
+    const int t_end = min(P.T, t_begin + P.tokens_per_split);
+    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
+    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < G * D; i += NT) {
+        const int g = i / D, d = i - g * D;
+        q_s[g * QP + (d >> 4) * C::QCH + (d & 15)] =
+            load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + (int64_t)h * G + g) * D + d) * P.qk_scale_log2;
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile_idx) {
+        const int s = tile_idx % S;
+        const int t0 = t_begin + tile_idx * kTile;
+        const int rows = min(kTile, t_end - t0);
+        uint8_t* sb = smem_raw + s * C::kStage;
+        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
+        mbar_expect_tx(&full[s], kb + vb);
+        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
+        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
+    }
+
+    const int kc = lane % LPR, kr = lane / LPR;
+    const int swz = G >= LPR ? kc * (G / LPR > 0 ? G / LPR : 1) : kc / (LPR / G > 0 ? LPR / G : 1);
+    const bool k_writer = G >= LPR || (kc % (LPR / G > 0 ? LPR / G : 1)) == 0;
+    const int vc = lane % LPRV, vrow = lane / LPRV;
+    const float* q_lane = q_s + kc * C::QCH;
+    float* p_w = p_s + warp * WR * G;
+    float* alpha_w = alpha_s + warp * G;
+
+    float acc[G][4], m_run[NREM], l_run[NREM];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[g][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NREM; ++j) { m_run[j] = -INFINITY; l_run[j] = 0.f; }
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % S;
+        if (tid == 0 && it + PD < n_tiles) {
+            const int nt = it + PD;  // goes into the stage tile nt - S used: every warp must have left it
+            if (nt >= S) { while (!mbar_try_wait(&empty[nt % S], ((nt / S) - 1) & 1)) {} }
+            issue(nt);
+        }
+        const int t0 = t_begin + it * kTile;
+        const int rows = min(kTile, t_end - t0);
+        // per-token scales of this lane's RT tokens (L1/L2-resident plain loads, consumed after the K phase)
+        float ksr[RT], vsr[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int row = warp * WR + r * RPP + kr;
+            ksr[r] = row < rows ? __ldg(P.k_scale + t0 + row) : 0.f;
+            vsr[r] = row < rows ? __ldg(P.v_scale + t0 + row) : 0.f;
+        }
+        while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
+        const uint8_t* sb = smem_raw + s * C::kStage;
+
+        // ---- K phase: [RT tokens x G heads] register block
+        uint32_t kw[RT][KW];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int row = warp * WR + r * RPP + kr;
+            const uint8_t* src = sb + row * C::kKRow + kc * (2 * KBITS);
+            if constexpr (KW == 4) {
+                const uint4 t = *reinterpret_cast<const uint4*>(src);
+                kw[r][0] = t.x; kw[r][1] = t.y; kw[r][2] = t.z; kw[r][3] = t.w;
+            } else {
+                const uint2 t = *reinterpret_cast<const uint2*>(src);
+                kw[r][0] = t.x; kw[r][1] = t.y;
+            }
+        }
+        float a[RT][G];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int j = 0; j < G; ++j) a[r][j] = 0.f;
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+            float f[RT][4];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) cvt4<KBITS>(kw[r], e4, f[r]);
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const float4 qq = *reinterpret_cast<const float4*>(q_lane + (j ^ swz) * QP + 4 * e4);
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    a[r][j] = fmaf(qq.x, f[r][0], a[r][j]); a[r][j] = fmaf(qq.y, f[r][1], a[r][j]);
+                    a[r][j] = fmaf(qq.z, f[r][2], a[r][j]); a[r][j] = fmaf(qq.w, f[r][3], a[r][j]);
+                }
+            }
+        }
+        // reduce-scatter over the LPR lanes of a row: register j of lane kc is head j ^ swz(kc), and swz maps lane bit o
+        // to the head bit that is halved away at that step, so the partner's upper half lands on my lower half
+        {
+            int n = G;
+#pragma unroll
+            for (int o = LPR / 2; o >= 1; o >>= 1) {
+                if (n > 1) {
+                    n >>= 1;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r)
+#pragma unroll
+                        for (int j = 0; j < G / 2; ++j)
+                            if (j < n) a[r][j] += __shfl_xor_sync(0xffffffffu, a[r][j + n], o);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) a[r][0] += __shfl_xor_sync(0xffffffffu, a[r][0], o);
+                }
+            }
+        }
+        // ---- softmax in registers: lane (kc, kr) holds the scores of head(s) j ^ swz for its RT tokens
+        bool moved = false;
+#pragma unroll
+        for (int j = 0; j < NREM; ++j) {
+            float mt = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int row = warp * WR + r * RPP + kr;
+                a[r][j] = row < rows ? a[r][j] * ksr[r] : -INFINITY;
+                mt = fmaxf(mt, a[r][j]);
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+            const float m_new = fmaxf(m_run[j], mt);
+            const float al = m_run[j] == -INFINITY ? 0.f : exp2f(m_run[j] - m_new);  // m_new == -inf only with m_run == -inf
+            moved |= m_new != m_run[j];
+            m_run[j] = m_new;
+            float lsum = 0.f;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const float pw = a[r][j] == -INFINITY ? 0.f : exp2f(a[r][j] - m_new);
+                lsum += pw;
+                if (k_writer) p_w[(r * RPP + kr) * G + (j ^ swz)] = pw * vsr[r];
+            }
+            l_run[j] = fmaf(l_run[j], al, lsum);
+            if (kr == 0 && k_writer) alpha_w[j ^ swz] = al;
+        }
+        moved = __any_sync(0xffffffffu, moved);
+        __syncwarp();
+
+        // ---- V phase: [G heads x 4 channels] accumulators
+        if (moved) {  // warp-uniform: the maxima settle after the first tiles
+#pragma unroll
+            for (int g4 = 0; g4 < G / 4; ++g4) {
+                const float4 al = *reinterpret_cast<const float4*>(alpha_w + 4 * g4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[4 * g4][e] *= al.x; acc[4 * g4 + 1][e] *= al.y; acc[4 * g4 + 2][e] *= al.z; acc[4 * g4 + 3][e] *= al.w;
+                }
+            }
+        }
+        const uint8_t* vsb = sb + C::kKTile + (warp * WR + vrow) * C::kVRow + vc * (4 * VBITS / 8);
+#pragma unroll 4
+        for (int ps = 0; ps < VP; ++ps) {
+            uint32_t vw[1];
+            if constexpr (VBITS == 8) vw[0] = *reinterpret_cast<const uint32_t*>(vsb + ps * VRW * C::kVRow);
+            else vw[0] = *reinterpret_cast<const unsigned short*>(vsb + ps * VRW * C::kVRow);
+            float f[4];
+            cvt4<VBITS>(vw, 0, f);
+            const float4* pr = reinterpret_cast<const float4*>(p_w + (ps * VRW + vrow) * G);
+#pragma unroll
+            for (int g4 = 0; g4 < G / 4; ++g4) {
+                const float4 pp = pr[g4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[4 * g4][e] = fmaf(pp.x, f[e], acc[4 * g4][e]);
+                    acc[4 * g4 + 1][e] = fmaf(pp.y, f[e], acc[4 * g4 + 1][e]);
+                    acc[4 * g4 + 2][e] = fmaf(pp.z, f[e], acc[4 * g4 + 2][e]);
+                    acc[4 * g4 + 3][e] = fmaf(pp.w, f[e], acc[4 * g4 + 3][e]);
+                }
+            }
+        }
+        __syncwarp();                       // p_w / alpha_w are rewritten by the next tile
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+    }
+
+    // ---- merge the warps' partials (own running max each) through shared memory; the ring is idle by now
+    float* red_s = reinterpret_cast<float*>(smem_raw);
+#pragma unroll
+    for (int j = 0; j < NREM; ++j) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) l_run[j] += __shfl_xor_sync(0xffffffffu, l_run[j], o);
+        if (kr == 0 && k_writer) { m_s[warp * G + (j ^ swz)] = m_run[j]; l_s[warp * G + (j ^ swz)] = l_run[j]; }
+    }
+    __syncthreads();  // also: every warp has finished reading the ring
+    float fac[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) M = fmaxf(M, m_s[w * G + g]);
+        const float mw = m_s[warp * G + g];
+        fac[g] = mw == -INFINITY ? 0.f : exp2f(mw - M);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        *reinterpret_cast<float4*>(red_s + ((warp * VRW + vrow) * G + g) * D + vc * 4) =
+            make_float4(acc[g][0] * fac[g], acc[g][1] * fac[g], acc[g][2] * fac[g], acc[g][3] * fac[g]);
+    __syncthreads();
+    for (int o = tid; o < G * D; o += NT) {
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < kWarps * VRW; ++r) sum += red_s[r * G * D + o];
+        const int g = o / D, d = o - g * D;
+        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
+        P.ws_acc[(hq * P.n_splits + split) * D + d] = sum;
+    }
+    if (tid < G) {
+        float M = -INFINITY, L = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) M = fmaxf(M, m_s[w * G + tid]);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const float mw = m_s[w * G + tid];
+            L += mw == -INFINITY ? 0.f : l_s[w * G + tid] * exp2f(mw - M);
+        }
+        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + tid;
+        P.ws_ml[(hq * P.n_splits + split) * 2] = M;
+        P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = L;
+    }
+}
+
 // Optional exact "current token" (the reference's decode step sees the new token's K/V unquantized:
 // benchmarker.py:473-477 concatenates them inside the model before they are quantized at :486): it is merged here
 // as one more split with m = q.k_cur * scale, l = 1, acc = v_cur.
@@ -916,14 +1236,33 @@ int launch_dp4a(dim3 grid, cudaStream_t st, const AttnParams& P) {
     return KVQ_OK;
 }
 
+template <int KBITS, int VBITS, int G, int D>
+int launch_gqa(dim3 grid, cudaStream_t st, const AttnParams& P) {
+    using C = GqaCfg<KBITS, VBITS, G, D>;
+    constexpr int NT = C::NT;
+    auto kern = decode_attn_gqa_kernel<KBITS, VBITS, G, D>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    KVQ_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        configured_dev = dev;
+    }
+    kern<<<grid, NT, C::kSmem, st>>>(P);
+    return KVQ_OK;
+}
+
 template <int KBITS, int VBITS, int G>
 int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
     if constexpr (G == 1) {  // MHA-shape decode: integer-dot variant (KVQ_ATTN_FP32=1 keeps the fp32 TMA variant for A/B runs)
         static const bool fp32_only = getenv("KVQ_ATTN_FP32") != nullptr;
         if (tma && !fp32_only) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
     }
-    if constexpr (G <= 2) {  // GQA groups of 4 / 8 are FMA-bound: the register-staged variant is faster there
+    if constexpr (G <= 2) {
         if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
+    } else {  // GQA groups of 4 / 8 are FFMA-bound: register-tiled variant (KVQ_ATTN_GQA_OLD=1 keeps the first version for A/B runs)
+        static const bool old_gqa = getenv("KVQ_ATTN_GQA_OLD") != nullptr;
+        if (tma && !old_gqa) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
     }
     if (D == 128) decode_attn_split_kernel<KBITS, VBITS, G, 128><<<grid, kThreads, 0, st>>>(P);
     else decode_attn_split_kernel<KBITS, VBITS, G, 64><<<grid, kThreads, 0, st>>>(P);
@@ -943,7 +1282,7 @@ int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool
 int choose_splits(int64_t B, int64_t H, int64_t T, int64_t G) {
     // TMA variant (G <= 2): one wave of 256-thread CTAs at KVQ_ATTN_CTAS_PER_SM per SM; register-staged variant
     // (G >= 4, 128-thread CTAs): four per SM
-    const int64_t target = (G <= 2 ? (int64_t)KVQ_ATTN_CTAS_PER_SM : 4) * sm_count();
+    const int64_t target = (G <= 2 ? (int64_t)KVQ_ATTN_CTAS_PER_SM : (int64_t)KVQ_ATTN_GQA_CTAS_PER_SM) * sm_count();
     int64_t n = (target + B * H - 1) / (B * H);
     const int64_t max_n = (T + 255) / 256;
     if (n > max_n) n = max_n;

@@ -159,7 +159,7 @@ def main():
     if "attn" in which:
         # C5 per-GPU shard at 8 GPUs: 1 KV head, B=8, T=65536, D=128; several layers rotate
         Ba, Ha, Ta, Da = 8, 1, 65536, 128
-        for G in (1, 8):
+        for G in [int(x) for x in os.environ.get("MB_ATTN_G", "1,8").split(",")]:
             for mode, kb, vb in (("mixed", 8, 4), ("int8", 8, 8), ("int4", 4, 4)):
                 nl = 6
                 kcs = [torch.randint(-127, 128, (Ba, Ha, Ta, Da if kb == 8 else Da // 2), device=dev, dtype=torch.int8) for _ in range(nl)]
