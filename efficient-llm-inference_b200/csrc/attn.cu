@@ -850,50 +850,94 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// packed fp32 pairs: Blackwell's FFMA2 / FADD2 / FMUL2 (PTX fma.rn.f32x2 ...) do two IEEE fp32 operations per issue slot;
+// a pair lives in a 64-bit register, and a pair whose halves are the same register becomes SASS's scalar-broadcast operand
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// lane bit o of the K-phase reduce-scatter -> head bit it halves away (bits >= 2 only; see the kernel)
+__host__ __device__ constexpr int gqa_swz(int kc, int G, int LPR) {
+    int s = 0, hb = G / 2;
+    for (int o = LPR / 2; o >= 1; o >>= 1) {
+        if (hb >= 2) { if (kc & o) s |= hb; hb >>= 1; }
+    }
+    return s;
+}
+
 template <int KBITS, int VBITS, int G, int D> struct GqaCfg {
     static constexpr int NT = kThreads2, kWarps = NT / 32, WR = kTile / kWarps;  // WR = 16 tokens per warp per tile
     static constexpr int kKRow = D * KBITS / 8, kVRow = D * VBITS / 8;
     static constexpr int kKTile = kTile * kKRow, kVTile = kTile * kVRow, kStage = kKTile + kVTile;
     static constexpr int kStages = KVQ_ATTN_GQA_STAGES;
     static constexpr int LPR = D / 16;                          // K: lanes per token row, 16 channels each
-    static constexpr int QCH = 20;                              // floats per 16-channel chunk of q (4 pad: conflict-free LDS.128)
-    static constexpr int QP = ((LPR * QCH + 31) / 32) * 32;     // q row pitch (floats)
+    // q in shared memory: [variant 2][chunk LPR][channel 16][G heads], padded so that the LPR lanes of a row, which read
+    // different chunks / variants / head groups in one LDS.128, hit 32 distinct banks (pads found by exhaustive search)
+    static constexpr int CP = 16 * G + (G == 8 && LPR == 8 ? 8 : 4);
+    static constexpr int VS = LPR * CP + (G == 8 && LPR == 4 ? 4 : 0);
     static constexpr int LPRV = D / 4, VRW = 32 / LPRV;         // V: lanes per token row (4 channels each), rows per warp pass
     static constexpr int kRed = kWarps * VRW * G * D * 4;       // final merge of the warps' partials aliases the ring
     static constexpr int kBuf = kStages * kStage > kRed ? kStages * kStage : kRed;
     // q_s, per-warp weight patches, per-warp alpha / m / l, barriers
-    static constexpr int kSmem = kBuf + G * QP * 4 + kWarps * WR * G * 4 + 3 * kWarps * G * 4 + 2 * kStages * 8 + 16;
+    static constexpr int kSmem = kBuf + 2 * VS * 4 + kWarps * WR * G * 4 + 3 * kWarps * G * 4 + 2 * kStages * 8 + 16;
 };
 
-// 4 consecutive codes -> 4 floats.  INT8: word e4 of the lane's words; INT4: half (e4 & 1) of word e4 >> 1
+// 4 consecutive codes -> 4 floats (two PRMT-built pairs, one FADD2 each).  INT8: word e4 of the lane's words; INT4: half
+// (e4 & 1) of word e4 >> 1
 template <int BITS> __device__ __forceinline__ void cvt4(const uint32_t* w, int e4, float f[4]) {
     if constexpr (BITS == 8) {
-        int8x4_to_float(w[e4], f);
+        const uint32_t x = w[e4] ^ 0x80808080u;
+        const f32x2 c = pack2(-8388736.f, -8388736.f);
+        const f32x2 lo = fadd2(pack2(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7651))), c);
+        const f32x2 hi = fadd2(pack2(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7652)), __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7653))), c);
+        unpack2(lo, f[0], f[1]);
+        unpack2(hi, f[2], f[3]);
     } else {
         const uint32_t x = w[e4 >> 1] >> (16 * (e4 & 1));
-        const uint32_t hi = (x >> 4) & 0x0f0fu, lo = x & 0x0f0fu;
-        f[0] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650)) - 8388616.f;
-        f[1] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650)) - 8388616.f;
-        f[2] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7651)) - 8388616.f;
-        f[3] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7651)) - 8388616.f;
+        const uint32_t hn = (x >> 4) & 0x0f0fu, ln = x & 0x0f0fu;
+        const f32x2 c = pack2(-8388616.f, -8388616.f);
+        const f32x2 lo = fadd2(pack2(__uint_as_float(__byte_perm(hn, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(ln, 0x4B000000u, 0x7650))), c);
+        const f32x2 hi = fadd2(pack2(__uint_as_float(__byte_perm(hn, 0x4B000000u, 0x7651)), __uint_as_float(__byte_perm(ln, 0x4B000000u, 0x7651))), c);
+        unpack2(lo, f[0], f[1]);
+        unpack2(hi, f[2], f[3]);
     }
 }
 
 template <int KBITS, int VBITS, int G, int D>
 __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_attn_gqa_kernel(AttnParams P) {
     using C = GqaCfg<KBITS, VBITS, G, D>;
-    constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR, QP = C::QP;
+    constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR;
     constexpr int LPR = C::LPR, RPP = 32 / LPR, RT = WR / RPP;  // K: rows per warp pass; register tile RT tokens x G heads
     constexpr int KW = 16 * KBITS / 32;                         // code words per lane per token
     constexpr int LPRV = C::LPRV, VRW = C::VRW, VP = WR / VRW;
     constexpr int NREM = G > LPR ? G / LPR : 1;                 // scores a lane holds per token after the reduce-scatter
     constexpr int S = C::kStages, PD = S > 2 ? S - 2 : 1;       // tiles in flight ahead of the math
+    constexpr int GP = G / 2;                                   // head pairs
     static_assert(G == 4 || G == 8, "G");
     static_assert(RT >= 1 && RT * RPP == WR, "tiling");
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);  // [G][QP], chunks of 16 channels padded to 20 floats
-    float* p_s = q_s + G * QP;                                  // [kWarps][WR][G] weights p * v_scale
+    float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);  // [2][LPR chunks][16][G] (padded): variant v holds head pos ^ 2v
+    float* p_s = q_s + 2 * C::VS;                               // [kWarps][WR][G] weights p * v_scale
     float* alpha_s = p_s + kWarps * WR * G;                     // [kWarps][G]
     float* m_s = alpha_s + kWarps * G;                          // [kWarps][G]  (end of kernel)
     float* l_s = m_s + kWarps * G;                              // [kWarps][G]  (end of kernel)
@@ -913,9 +957,9 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < G * D; i += NT) {
-        const int g = i / D, d = i - g * D;
-        q_s[g * QP + (d >> 4) * C::QCH + (d & 15)] =
+    for (int i = tid; i < 2 * G * D; i += NT) {
+        const int v = i / (G * D), r = i - v * G * D, g = r / D, d = r - g * D;
+        q_s[v * C::VS + (d >> 4) * C::CP + (d & 15) * G + (g ^ (2 * v))] =
             load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + (int64_t)h * G + g) * D + d) * P.qk_scale_log2;
     }
     __syncthreads();
@@ -934,19 +978,34 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
         for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
     }
 
+    // K-phase lane roles.  Register j of lane kc holds head j ^ swz: swz maps every lane bit whose reduce-scatter step halves away a
+    // head bit >= 2 to that head bit, so those steps exchange statically indexed register PAIRS; head bit 1 is scattered with a select.
     const int kc = lane % LPR, kr = lane / LPR;
-    const int swz = G >= LPR ? kc * (G / LPR > 0 ? G / LPR : 1) : kc / (LPR / G > 0 ? LPR / G : 1);
-    const bool k_writer = G >= LPR || (kc % (LPR / G > 0 ? LPR / G : 1)) == 0;
+    const int swz = gqa_swz(kc, G, LPR);
+    int sel_bit = 0, bfly_mask = 0;
+    {
+        int hb = G / 2;
+#pragma unroll
+        for (int o = LPR / 2; o >= 1; o >>= 1) {
+            if (hb >= 2) hb >>= 1;
+            else if (hb == 1) { sel_bit = o; hb = 0; }
+            else bfly_mask |= o;
+        }
+    }
+    const bool k_writer = (kc & bfly_mask) == 0;
+    const int head0 = swz | ((sel_bit && (kc & sel_bit)) ? 1 : 0);  // head of score 0 (score 1, if NREM == 2, is head0 + 1)
     const int vc = lane % LPRV, vrow = lane / LPRV;
-    const float* q_lane = q_s + kc * C::QCH;
+    const float* q_lane = q_s + ((swz >> 1) & 1) * C::VS + kc * C::CP;
+    const int mm = swz >> 2;
     float* p_w = p_s + warp * WR * G;
     float* alpha_w = alpha_s + warp * G;
 
-    float acc[G][4], m_run[NREM], l_run[NREM];
+    f32x2 acc[GP][4];  // (head 2gp, head 2gp + 1) x 4 channels
+    float m_run[NREM], l_run[NREM];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+    for (int g = 0; g < GP; ++g)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[g][e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[g][e] = 0ull;
 #pragma unroll
     for (int j = 0; j < NREM; ++j) { m_run[j] = -INFINITY; l_run[j] = 0.f; }
 
@@ -970,7 +1029,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
         while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
         const uint8_t* sb = smem_raw + s * C::kStage;
 
-        // ---- K phase: [RT tokens x G heads] register block
+        // ---- K phase: [RT tokens x G heads] register block, two heads per FFMA2
         uint32_t kw[RT][KW];
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
@@ -984,46 +1043,64 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
                 kw[r][0] = t.x; kw[r][1] = t.y;
             }
         }
-        float a[RT][G];
+        f32x2 a[RT][GP];
 #pragma unroll
         for (int r = 0; r < RT; ++r)
 #pragma unroll
-            for (int j = 0; j < G; ++j) a[r][j] = 0.f;
+            for (int j = 0; j < GP; ++j) a[r][j] = 0ull;
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
             float f[RT][4];
 #pragma unroll
             for (int r = 0; r < RT; ++r) cvt4<KBITS>(kw[r], e4, f[r]);
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-                const float4 qq = *reinterpret_cast<const float4*>(q_lane + (j ^ swz) * QP + 4 * e4);
+            for (int ee = 0; ee < 4; ++ee) {
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    a[r][j] = fmaf(qq.x, f[r][0], a[r][j]); a[r][j] = fmaf(qq.y, f[r][1], a[r][j]);
-                    a[r][j] = fmaf(qq.z, f[r][2], a[r][j]); a[r][j] = fmaf(qq.w, f[r][3], a[r][j]);
+                for (int m = 0; m < G / 4; ++m) {
+                    const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + ee) * G + 4 * (m ^ mm));
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const f32x2 fb = pack2(f[r][ee], f[r][ee]);
+                        a[r][2 * m] = ffma2(qq.x, fb, a[r][2 * m]);
+                        a[r][2 * m + 1] = ffma2(qq.y, fb, a[r][2 * m + 1]);
+                    }
                 }
             }
         }
-        // reduce-scatter over the LPR lanes of a row: register j of lane kc is head j ^ swz(kc), and swz maps lane bit o
-        // to the head bit that is halved away at that step, so the partner's upper half lands on my lower half
+        // reduce-scatter over the LPR lanes of a row
+        float sc[RT][NREM];
         {
-            int n = G;
+            int hb = G / 2;
+            bool scalar = false;
 #pragma unroll
             for (int o = LPR / 2; o >= 1; o >>= 1) {
-                if (n > 1) {
-                    n >>= 1;
+                if (hb >= 2) {         // partner's upper half of the pairs lands on my lower half
+                    hb >>= 1;
 #pragma unroll
                     for (int r = 0; r < RT; ++r)
 #pragma unroll
-                        for (int j = 0; j < G / 2; ++j)
-                            if (j < n) a[r][j] += __shfl_xor_sync(0xffffffffu, a[r][j + n], o);
+                        for (int j = 0; j < GP / 2; ++j)
+                            if (j < hb) a[r][j] = fadd2(a[r][j], __shfl_xor_sync(0xffffffffu, a[r][j + hb], o));
+                } else if (hb == 1) {  // last pair: keep one head, send the other
+                    hb = 0; scalar = true;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        float x, y;
+                        unpack2(a[r][0], x, y);
+                        const bool up = (kc & o) != 0;
+                        sc[r][0] = (up ? y : x) + __shfl_xor_sync(0xffffffffu, up ? x : y, o);
+                    }
                 } else {
 #pragma unroll
-                    for (int r = 0; r < RT; ++r) a[r][0] += __shfl_xor_sync(0xffffffffu, a[r][0], o);
+                    for (int r = 0; r < RT; ++r) sc[r][0] += __shfl_xor_sync(0xffffffffu, sc[r][0], o);
                 }
             }
+            if (!scalar) {  // G > LPR: a pair of heads per lane
+#pragma unroll
+                for (int r = 0; r < RT; ++r) unpack2(a[r][0], sc[r][0], sc[r][NREM - 1]);
+            }
         }
-        // ---- softmax in registers: lane (kc, kr) holds the scores of head(s) j ^ swz for its RT tokens
+        // ---- softmax in registers: lane (kc, kr) holds the scores of head0 (+ j) for its RT tokens
         bool moved = false;
 #pragma unroll
         for (int j = 0; j < NREM; ++j) {
@@ -1031,8 +1108,8 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
                 const int row = warp * WR + r * RPP + kr;
-                a[r][j] = row < rows ? a[r][j] * ksr[r] : -INFINITY;
-                mt = fmaxf(mt, a[r][j]);
+                sc[r][j] = row < rows ? sc[r][j] * ksr[r] : -INFINITY;
+                mt = fmaxf(mt, sc[r][j]);
             }
 #pragma unroll
             for (int o = LPR; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
@@ -1043,25 +1120,23 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
             float lsum = 0.f;
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
-                const float pw = a[r][j] == -INFINITY ? 0.f : exp2f(a[r][j] - m_new);
+                const float pw = sc[r][j] == -INFINITY ? 0.f : exp2f(sc[r][j] - m_new);
                 lsum += pw;
-                if (k_writer) p_w[(r * RPP + kr) * G + (j ^ swz)] = pw * vsr[r];
+                if (k_writer) p_w[(r * RPP + kr) * G + head0 + j] = pw * vsr[r];
             }
             l_run[j] = fmaf(l_run[j], al, lsum);
-            if (kr == 0 && k_writer) alpha_w[j ^ swz] = al;
+            if (kr == 0 && k_writer) alpha_w[head0 + j] = al;
         }
         moved = __any_sync(0xffffffffu, moved);
         __syncwarp();
 
-        // ---- V phase: [G heads x 4 channels] accumulators
+        // ---- V phase: [G heads x 4 channels] accumulators, two heads per FFMA2
         if (moved) {  // warp-uniform: the maxima settle after the first tiles
 #pragma unroll
             for (int g4 = 0; g4 < G / 4; ++g4) {
-                const float4 al = *reinterpret_cast<const float4*>(alpha_w + 4 * g4);
+                const ulonglong2 al = *reinterpret_cast<const ulonglong2*>(alpha_w + 4 * g4);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    acc[4 * g4][e] *= al.x; acc[4 * g4 + 1][e] *= al.y; acc[4 * g4 + 2][e] *= al.z; acc[4 * g4 + 3][e] *= al.w;
-                }
+                for (int e = 0; e < 4; ++e) { acc[2 * g4][e] = fmul2(acc[2 * g4][e], al.x); acc[2 * g4 + 1][e] = fmul2(acc[2 * g4 + 1][e], al.y); }
             }
         }
         const uint8_t* vsb = sb + C::kKTile + (warp * WR + vrow) * C::kVRow + vc * (4 * VBITS / 8);
@@ -1072,20 +1147,19 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
             else vw[0] = *reinterpret_cast<const unsigned short*>(vsb + ps * VRW * C::kVRow);
             float f[4];
             cvt4<VBITS>(vw, 0, f);
-            const float4* pr = reinterpret_cast<const float4*>(p_w + (ps * VRW + vrow) * G);
+            const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(p_w + (ps * VRW + vrow) * G);
 #pragma unroll
             for (int g4 = 0; g4 < G / 4; ++g4) {
-                const float4 pp = pr[g4];
+                const ulonglong2 pp = pr[g4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    acc[4 * g4][e] = fmaf(pp.x, f[e], acc[4 * g4][e]);
-                    acc[4 * g4 + 1][e] = fmaf(pp.y, f[e], acc[4 * g4 + 1][e]);
-                    acc[4 * g4 + 2][e] = fmaf(pp.z, f[e], acc[4 * g4 + 2][e]);
-                    acc[4 * g4 + 3][e] = fmaf(pp.w, f[e], acc[4 * g4 + 3][e]);
+                    const f32x2 fb = pack2(f[e], f[e]);
+                    acc[2 * g4][e] = ffma2(pp.x, fb, acc[2 * g4][e]);
+                    acc[2 * g4 + 1][e] = ffma2(pp.y, fb, acc[2 * g4 + 1][e]);
                 }
             }
         }
-        __syncwarp();                       // p_w / alpha_w are rewritten by the next tile
+        __syncwarp();                           // p_w / alpha_w are rewritten by the next tile
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
     }
 
@@ -1095,22 +1169,28 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     for (int j = 0; j < NREM; ++j) {
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) l_run[j] += __shfl_xor_sync(0xffffffffu, l_run[j], o);
-        if (kr == 0 && k_writer) { m_s[warp * G + (j ^ swz)] = m_run[j]; l_s[warp * G + (j ^ swz)] = l_run[j]; }
+        if (kr == 0 && k_writer) { m_s[warp * G + head0 + j] = m_run[j]; l_s[warp * G + head0 + j] = l_run[j]; }
     }
     __syncthreads();  // also: every warp has finished reading the ring
-    float fac[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        float M = -INFINITY;
+    for (int gp = 0; gp < GP; ++gp) {
+        float fac[2];
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) M = fmaxf(M, m_s[w * G + g]);
-        const float mw = m_s[warp * G + g];
-        fac[g] = mw == -INFINITY ? 0.f : exp2f(mw - M);
+        for (int u = 0; u < 2; ++u) {
+            const int g = 2 * gp + u;
+            float M = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) M = fmaxf(M, m_s[w * G + g]);
+            const float mw = m_s[warp * G + g];
+            fac[u] = mw == -INFINITY ? 0.f : exp2f(mw - M);
+        }
+        float lo[4], hi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) unpack2(acc[gp][e], lo[e], hi[e]);
+        float* dst = red_s + ((warp * VRW + vrow) * G + 2 * gp) * D + vc * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(lo[0] * fac[0], lo[1] * fac[0], lo[2] * fac[0], lo[3] * fac[0]);
+        *reinterpret_cast<float4*>(dst + D) = make_float4(hi[0] * fac[1], hi[1] * fac[1], hi[2] * fac[1], hi[3] * fac[1]);
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-        *reinterpret_cast<float4*>(red_s + ((warp * VRW + vrow) * G + g) * D + vc * 4) =
-            make_float4(acc[g][0] * fac[g], acc[g][1] * fac[g], acc[g][2] * fac[g], acc[g][3] * fac[g]);
     __syncthreads();
     for (int o = tid; o < G * D; o += NT) {
         float sum = 0.f;
