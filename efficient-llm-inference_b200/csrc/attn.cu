@@ -845,6 +845,14 @@ __global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams 
 #ifndef KVQ_ATTN_GQA_CTAS_PER_SM
 #define KVQ_ATTN_GQA_CTAS_PER_SM 2
 #endif
+#ifndef KVQ_ATTN_GQA_RT
+#define KVQ_ATTN_GQA_RT 4
+#endif
+#ifndef KVQ_ATTN_GQA_VUNROLL
+#define KVQ_ATTN_GQA_VUNROLL 8
+#endif
+
+constexpr float kLazyLog2 = 8.f;  // see the softmax step of decode_attn_gqa_kernel
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -926,14 +934,16 @@ template <int KBITS, int VBITS, int G, int D>
 __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_attn_gqa_kernel(AttnParams P) {
     using C = GqaCfg<KBITS, VBITS, G, D>;
     constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR;
-    constexpr int LPR = C::LPR, RPP = 32 / LPR, RT = WR / RPP;  // K: rows per warp pass; register tile RT tokens x G heads
+    constexpr int LPR = C::LPR, RPP = 32 / LPR, RTT = WR / RPP;  // K: rows per warp pass, tokens per lane per tile
+    constexpr int RT = RTT < KVQ_ATTN_GQA_RT ? RTT : KVQ_ATTN_GQA_RT, KSUB = RTT / RT;  // register tile: RT tokens x G heads
     constexpr int KW = 16 * KBITS / 32;                         // code words per lane per token
     constexpr int LPRV = C::LPRV, VRW = C::VRW, VP = WR / VRW;
     constexpr int NREM = G > LPR ? G / LPR : 1;                 // scores a lane holds per token after the reduce-scatter
     constexpr int S = C::kStages, PD = S > 2 ? S - 2 : 1;       // tiles in flight ahead of the math
     constexpr int GP = G / 2;                                   // head pairs
+    constexpr int kVUnroll = KVQ_ATTN_GQA_VUNROLL;
     static_assert(G == 4 || G == 8, "G");
-    static_assert(RT >= 1 && RT * RPP == WR, "tiling");
+    static_assert(RT >= 1 && RT * KSUB * RPP == WR, "tiling");
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);  // [2][LPR chunks][16][G] (padded): variant v holds head pos ^ 2v
@@ -1019,9 +1029,9 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
         const int t0 = t_begin + it * kTile;
         const int rows = min(kTile, t_end - t0);
         // per-token scales of this lane's RT tokens (L1/L2-resident plain loads, consumed after the K phase)
-        float ksr[RT], vsr[RT];
+        float ksr[RTT], vsr[RTT];
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
+        for (int r = 0; r < RTT; ++r) {
             const int row = warp * WR + r * RPP + kr;
             ksr[r] = row < rows ? __ldg(P.k_scale + t0 + row) : 0.f;
             vsr[r] = row < rows ? __ldg(P.v_scale + t0 + row) : 0.f;
@@ -1029,47 +1039,48 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
         while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
         const uint8_t* sb = smem_raw + s * C::kStage;
 
-        // ---- K phase: [RT tokens x G heads] register block, two heads per FFMA2
-        uint32_t kw[RT][KW];
+        // ---- K phase: [RT tokens x G heads] register blocks, two heads per FFMA2
+        float sc[RTT][NREM];
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const int row = warp * WR + r * RPP + kr;
-            const uint8_t* src = sb + row * C::kKRow + kc * (2 * KBITS);
-            if constexpr (KW == 4) {
-                const uint4 t = *reinterpret_cast<const uint4*>(src);
-                kw[r][0] = t.x; kw[r][1] = t.y; kw[r][2] = t.z; kw[r][3] = t.w;
-            } else {
-                const uint2 t = *reinterpret_cast<const uint2*>(src);
-                kw[r][0] = t.x; kw[r][1] = t.y;
+        for (int sub = 0; sub < KSUB; ++sub) {
+            uint32_t kw[RT][KW];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int row = warp * WR + (sub * RT + r) * RPP + kr;
+                const uint8_t* src = sb + row * C::kKRow + kc * (2 * KBITS);
+                if constexpr (KW == 4) {
+                    const uint4 t = *reinterpret_cast<const uint4*>(src);
+                    kw[r][0] = t.x; kw[r][1] = t.y; kw[r][2] = t.z; kw[r][3] = t.w;
+                } else {
+                    const uint2 t = *reinterpret_cast<const uint2*>(src);
+                    kw[r][0] = t.x; kw[r][1] = t.y;
+                }
             }
-        }
-        f32x2 a[RT][GP];
+            f32x2 a[RT][GP];
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
+            for (int r = 0; r < RT; ++r)
 #pragma unroll
-            for (int j = 0; j < GP; ++j) a[r][j] = 0ull;
+                for (int j = 0; j < GP; ++j) a[r][j] = 0ull;
 #pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-            float f[RT][4];
+            for (int e4 = 0; e4 < 4; ++e4) {
+                float f[RT][4];
 #pragma unroll
-            for (int r = 0; r < RT; ++r) cvt4<KBITS>(kw[r], e4, f[r]);
+                for (int r = 0; r < RT; ++r) cvt4<KBITS>(kw[r], e4, f[r]);
 #pragma unroll
-            for (int ee = 0; ee < 4; ++ee) {
+                for (int ee = 0; ee < 4; ++ee) {
 #pragma unroll
-                for (int m = 0; m < G / 4; ++m) {
-                    const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + ee) * G + 4 * (m ^ mm));
+                    for (int m = 0; m < G / 4; ++m) {
+                        const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + ee) * G + 4 * (m ^ mm));
 #pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const f32x2 fb = pack2(f[r][ee], f[r][ee]);
-                        a[r][2 * m] = ffma2(qq.x, fb, a[r][2 * m]);
-                        a[r][2 * m + 1] = ffma2(qq.y, fb, a[r][2 * m + 1]);
+                        for (int r = 0; r < RT; ++r) {
+                            const f32x2 fb = pack2(f[r][ee], f[r][ee]);
+                            a[r][2 * m] = ffma2(qq.x, fb, a[r][2 * m]);
+                            a[r][2 * m + 1] = ffma2(qq.y, fb, a[r][2 * m + 1]);
+                        }
                     }
                 }
             }
-        }
-        // reduce-scatter over the LPR lanes of a row
-        float sc[RT][NREM];
-        {
+            // reduce-scatter over the LPR lanes of a row
             int hb = G / 2;
             bool scalar = false;
 #pragma unroll
@@ -1088,46 +1099,56 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
                         float x, y;
                         unpack2(a[r][0], x, y);
                         const bool up = (kc & o) != 0;
-                        sc[r][0] = (up ? y : x) + __shfl_xor_sync(0xffffffffu, up ? x : y, o);
+                        sc[sub * RT + r][0] = (up ? y : x) + __shfl_xor_sync(0xffffffffu, up ? x : y, o);
                     }
                 } else {
 #pragma unroll
-                    for (int r = 0; r < RT; ++r) sc[r][0] += __shfl_xor_sync(0xffffffffu, sc[r][0], o);
+                    for (int r = 0; r < RT; ++r) sc[sub * RT + r][0] += __shfl_xor_sync(0xffffffffu, sc[sub * RT + r][0], o);
                 }
             }
             if (!scalar) {  // G > LPR: a pair of heads per lane
 #pragma unroll
-                for (int r = 0; r < RT; ++r) unpack2(a[r][0], sc[r][0], sc[r][NREM - 1]);
+                for (int r = 0; r < RT; ++r) unpack2(a[r][0], sc[sub * RT + r][0], sc[sub * RT + r][NREM - 1]);
             }
         }
         // ---- softmax in registers: lane (kc, kr) holds the scores of head0 (+ j) for its RT tokens
         bool moved = false;
+        float alj[NREM];
 #pragma unroll
         for (int j = 0; j < NREM; ++j) {
             float mt = -INFINITY;
 #pragma unroll
-            for (int r = 0; r < RT; ++r) {
+            for (int r = 0; r < RTT; ++r) {
                 const int row = warp * WR + r * RPP + kr;
                 sc[r][j] = row < rows ? sc[r][j] * ksr[r] : -INFINITY;
                 mt = fmaxf(mt, sc[r][j]);
             }
 #pragma unroll
             for (int o = LPR; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-            const float m_new = fmaxf(m_run[j], mt);
-            const float al = m_run[j] == -INFINITY ? 0.f : exp2f(m_run[j] - m_new);  // m_new == -inf only with m_run == -inf
-            moved |= m_new != m_run[j];
+            // lazy reference: the running reference only moves when the tile maximum exceeds it by more than 2^kLazyLog2 (weights
+            // stay <= 2^kLazyLog2, harmless in fp32; the result does not depend on the reference), so the accumulators are
+            // rescaled a handful of times per split instead of after ~70 % of the tiles
+            const float m_old = m_run[j];
+            const bool up = mt > m_old + kLazyLog2;  // false when the warp's rows are all masked (mt == -inf)
+            const float m_new = up ? mt : m_old;
+            const float al = up ? (m_old == -INFINITY ? 0.f : exp2f(m_old - m_new)) : 1.f;
+            moved |= up;
             m_run[j] = m_new;
             float lsum = 0.f;
 #pragma unroll
-            for (int r = 0; r < RT; ++r) {
+            for (int r = 0; r < RTT; ++r) {
                 const float pw = sc[r][j] == -INFINITY ? 0.f : exp2f(sc[r][j] - m_new);
                 lsum += pw;
                 if (k_writer) p_w[(r * RPP + kr) * G + head0 + j] = pw * vsr[r];
             }
             l_run[j] = fmaf(l_run[j], al, lsum);
-            if (kr == 0 && k_writer) alpha_w[head0 + j] = al;
+            alj[j] = al;
         }
         moved = __any_sync(0xffffffffu, moved);
+        if (moved && kr == 0 && k_writer) {
+#pragma unroll
+            for (int j = 0; j < NREM; ++j) alpha_w[head0 + j] = alj[j];
+        }
         __syncwarp();
 
         // ---- V phase: [G heads x 4 channels] accumulators, two heads per FFMA2
@@ -1140,7 +1161,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
             }
         }
         const uint8_t* vsb = sb + C::kKTile + (warp * WR + vrow) * C::kVRow + vc * (4 * VBITS / 8);
-#pragma unroll 4
+#pragma unroll kVUnroll
         for (int ps = 0; ps < VP; ++ps) {
             uint32_t vw[1];
             if constexpr (VBITS == 8) vw[0] = *reinterpret_cast<const uint32_t*>(vsb + ps * VRW * C::kVRow);
