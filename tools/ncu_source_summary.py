@@ -11,6 +11,8 @@ stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued
 ops, st, samp = collections.Counter(), collections.Counter(), collections.Counter()
 tot = 0
 for r in rows[hi + 1:]:
+    if len(r) <= max(ci, ei, si):
+        continue
     try:
         n = int(r[ei])
     except ValueError:
