@@ -140,3 +140,40 @@ def test_composed_quant_plus_sliding_window(bench):
     assert big[0] == bench.generate_with_quantized_kv(PROMPT, 6, mode="mixed", fused_attention=True)[0]
     with pytest.raises(ValueError):
         bench.generate_with_quantized_kv(PROMPT, 2, mode="mixed", evict=ev)
+
+
+@pytest.mark.parametrize("kv_heads,head_dim", [(2, 64), (1, 128)])  # G = 4 at D = 64; G = 8 at D = 128 (Llama-3-70B's grouping)
+def test_fused_attention_on_a_gqa_model(kv_heads, head_dim):
+    """SURVEY 8f-1 on a grouped-query model (random-init Llama: RoPE keys, num_key_value_heads < num_attention_heads): the
+    register-tiled GQA kernel behind the HF attention interface vs the reference-style dequantize-everything loop."""
+    from transformers import DynamicCache, LlamaConfig, LlamaForCausalLM
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    from kvq_b200.hf_cache import KvqFusedCache, fused_attention
+    from kvq_b200.quantization import QuantizedKVCache
+    torch.manual_seed(1)
+    cfg = LlamaConfig(hidden_size=8 * head_dim, intermediate_size=512, num_hidden_layers=2, num_attention_heads=8,
+                      num_key_value_heads=kv_heads, head_dim=head_dim, vocab_size=1000, max_position_embeddings=512)
+    model = LlamaForCausalLM(cfg).half().cuda().eval()
+    ids = StubTokenizer(batch=2)(PROMPT * 2).input_ids.cuda()  # 176 tokens: more than one 128-token tile
+    for mode in ("int8", "mixed"):
+        out = model(input_ids=ids, use_cache=True)
+        kv = tuple((l.keys, l.values) for l in out.past_key_values.layers)
+        assert kv[0][0].shape[1] == kv_heads
+        qc = QuantizedKVCache(n_layers=len(kv), mode=mode, device="cuda", compute_dtype=torch.float16)
+        qc.init_from_prompt_past(kv)
+        nxt = torch.argmax(out.logits[:, -1, :], dim=-1, keepdim=True)
+        ref = model(input_ids=nxt, use_cache=True, past_key_values=DynamicCache(ddp_cache_data=qc.to_past_key_values()))
+        cache = KvqFusedCache(len(kv), mode=mode, compute_dtype=torch.float16)
+        with fused_attention(model):
+            out2 = model(input_ids=ids, use_cache=True, past_key_values=cache)
+            torch.testing.assert_close(out2.logits.float(), out.logits.float(), rtol=2e-2, atol=2e-2)
+            for a, b in zip(cache.layers, qc.layers):
+                assert torch.equal(a.store.quantized()[0], b.quantized()[0]) and torch.equal(a.store.quantized()[3], b.quantized()[3])
+            got = model(input_ids=nxt, use_cache=True, past_key_values=cache)
+        torch.testing.assert_close(got.logits.float(), ref.logits.float(), rtol=2e-2, atol=2e-2)
+    b = KVCacheBenchmarker(model, StubTokenizer(), device="cuda")
+    t_fused = b.generate_with_quantized_kv(PROMPT, 8, mode="mixed", fused_attention=True)
+    t_plain = b.generate_with_quantized_kv(PROMPT, 8, mode="mixed")
+    assert t_fused[1] == t_plain[1] == 8 and t_fused[2] == t_plain[2]
+    agree = sum(x == y for x, y in zip(t_fused[0].split(), t_plain[0].split())) / len(t_plain[0].split())
+    assert agree >= 0.95
