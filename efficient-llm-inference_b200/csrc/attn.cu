@@ -1236,6 +1236,298 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     }
 }
 
+// =====================================================================================================
+// Per-warp integer-dot variant for G == 1 (replaces decode_attn_dp4a_kernel as the default MHA-shape kernel).
+// Same arithmetic as the block-wide DP4A kernel above -- q as three signed byte planes, weights p * v_scale[t] as
+// three unsigned byte planes, int32 accumulators flushed when the softmax reference moves -- restructured like the
+// GQA kernel: every warp runs its own online softmax over its own 16 tokens of each 128-token tile, so the main loop
+// has no block-wide barrier (the block-wide kernel: 2 per tile, no eligible warp in 50 % of the cycles), and
+//   * the D/16 partial dot products of a row are combined by a reduce-scatter over the FOUR rows a lane group works on
+//     (register j of lane kc holds pass j ^ (kc >> 1): 4 SHFL + 4 FADD instead of 12 + 12);
+//   * each token's score ends in two lanes: one k_scale / v_scale load per lane per tile, warp max by REDUX on the
+//     order-preserving integer image of the float;
+//   * lazy reference (moves only when exceeded by 2^kMhaLazyLog2; weights are scaled so that 2^kMhaLazyLog2 * max(v_scale)
+//     still fits the 24-bit fixed point: 21 bits left for weights <= 1), so the int32 -> fp32 flush is rare.
+// =====================================================================================================
+
+#ifndef KVQ_ATTN_MHA_STAGES
+#define KVQ_ATTN_MHA_STAGES 3
+#endif
+#ifndef KVQ_ATTN_MHA_CTAS_PER_SM
+#define KVQ_ATTN_MHA_CTAS_PER_SM 2
+#endif
+constexpr float kMhaLazyLog2 = 3.f;
+
+__device__ __forceinline__ int float_order_key(float x) {  // monotone float -> int (an involution on the bit pattern)
+    const int b = __float_as_int(x);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+
+template <int KBITS, int VBITS, int D> struct MhaCfg {
+    static constexpr int NT = kThreads2, kWarps = NT / 32, WR = kTile / kWarps;  // 16 tokens per warp per tile
+    static constexpr int kKRow = D * KBITS / 8, kVRow = D * VBITS / 8;
+    static constexpr int kKTile = kTile * kKRow, kVTile = kTile * kVRow, kStage = kKTile + kVTile;
+    static constexpr int kStages = KVQ_ATTN_MHA_STAGES;
+    static constexpr int WPR = D / 8, HW = 32 / WPR;            // V: lanes per token row (8 channels each); row groups per warp
+    static constexpr int kRed = kWarps * HW * D * 4;            // final merge of the partials aliases the ring
+    static constexpr int kBuf = kStages * kStage > kRed ? kStages * kStage : kRed;
+    // weight digit patches [kWarps][3][16], q digits [3][D], per-warp m / l, block scratch, barriers
+    static constexpr int kSmem = kBuf + kWarps * 48 + 3 * D + 2 * kWarps * 4 + 2 * kWarps * 4 + 2 * kStages * 8 + 32;
+};
+
+template <int KBITS, int VBITS, int D>
+__global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_attn_mha_kernel(AttnParams P) {
+    using C = MhaCfg<KBITS, VBITS, D>;
+    constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR;
+    constexpr int LPR = D / 16, RPP = 32 / LPR, RTT = WR / RPP;  // K: lanes per row, rows per warp pass, passes (4 / 2)
+    constexpr int WPR = C::WPR, HW = C::HW, GPH = 4 / HW;       // V: groups of four tokens per row group (2 / 1)
+    constexpr int VB = 8 * VBITS / 8;                           // bytes a lane reads per V row: 8 (INT8) / 4 (INT4)
+    constexpr int S = C::kStages, PD = S > 2 ? S - 2 : 1;
+    static_assert(RTT == 4 || RTT == 2, "passes");
+
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* wq_s = smem_raw + C::kBuf;                                  // [kWarps][3][16] weight digits
+    int8_t* qd_s = reinterpret_cast<int8_t*>(wq_s + kWarps * 48);        // [3][D] q digits
+    float* m_s = reinterpret_cast<float*>(qd_s + 3 * D);                 // [kWarps]
+    float* l_s = m_s + kWarps;                                           // [kWarps]
+    float* scr_s = l_s + kWarps;                                         // [2][kWarps] setup scratch
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(scr_s + 2 * kWarps) + 7) & ~uintptr_t(7));
+    uint64_t* empty = full + S;
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t_begin = split * P.tokens_per_split;
+    const int t_end = min(P.T, t_begin + P.tokens_per_split);
+    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
+    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto issue = [&](int tile_idx) {
+        const int s = tile_idx % S;
+        const int t0 = t_begin + tile_idx * kTile;
+        const int rows = min(kTile, t_end - t0);
+        uint8_t* sb = smem_raw + s * C::kStage;
+        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
+        mbar_expect_tx(&full[s], kb + vb);
+        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
+        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+    };
+    __syncthreads();  // barriers initialised before the first bulk copy can complete on them
+    if (tid == 0) {
+        for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
+    }
+
+    // ---- setup: q -> 24-bit fixed point (three signed byte planes); max v_scale of the split
+    float qv = 0.f;
+    if (tid < D) qv = load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + h) * D + tid) * P.qk_scale_log2;
+    float vmax = 0.f;
+    for (int t = t_begin + tid; t < t_end; t += NT * 8) {  // 8 independent loads in flight
+        float v8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v8[u] = t + u * NT < t_end ? __ldg(P.v_scale + t + u * NT) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) vmax = fmaxf(vmax, v8[u]);
+    }
+    float qa = fabsf(qv);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { qa = fmaxf(qa, __shfl_xor_sync(0xffffffffu, qa, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); }
+    if (lane == 0) { scr_s[warp] = qa; scr_s[kWarps + warp] = vmax; }
+    __syncthreads();
+    float qmax = 0.f, vsmax = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < kWarps; ++w8) { qmax = fmaxf(qmax, scr_s[w8]); vsmax = fmaxf(vsmax, scr_s[kWarps + w8]); }
+    const float dq = qmax > 0.f ? qmax / kFixedMax : 1.f;                                    // q = Q * dq
+    const float dw = vsmax > 0.f ? vsmax * exp2f(kMhaLazyLog2) / kFixedMax : 1.f;            // weight = W * dw, weights <= 2^lazy * vsmax
+    const float inv_dw = 1.f / dw;
+    if (tid < D) {
+        const int Q = __float2int_rn(qv / dq);
+        const int d0 = ((Q + 128) & 255) - 128, Q1 = (Q - d0) >> 8;
+        const int d1 = ((Q1 + 128) & 255) - 128, d2 = (Q1 - d1) >> 8;
+        qd_s[tid] = (int8_t)d0; qd_s[D + tid] = (int8_t)d1; qd_s[2 * D + tid] = (int8_t)d2;
+    }
+    __syncthreads();
+
+    // K-phase lane roles: kc = 16-channel chunk, kr = row of the pass; register j of the lane is pass j ^ swzp
+    const int kc = lane % LPR, kr = lane / LPR;
+    const int swzp = kc >> 1;
+    const int my_row = warp * WR + swzp * RPP + kr;  // the token (row of the tile) whose score this lane ends up with
+    const bool s_writer = (kc & 1) == 0;             // lanes kc and kc ^ 1 hold the same token
+    // V-phase lane roles: 8 channels of a row; row group hw takes the token groups hw * GPH ..
+    const int vc = lane % WPR, hw = lane / WPR;
+    uint8_t* wq_w = wq_s + warp * 48;
+
+    uint32_t qk[3][4];  // this lane's 16 channels of q, three planes x four words, in the element order of the K words
+    int kinit[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const uint4 t = *reinterpret_cast<const uint4*>(qd_s + pl * D + kc * 16);
+        if (KBITS == 8) { qk[pl][0] = t.x; qk[pl][1] = t.y; qk[pl][2] = t.z; qk[pl][3] = t.w; kinit[pl] = 0; }
+        else {
+            // INT4 rows: word j holds elements 8j..8j+7, high nibbles = even elements, low = odd
+            qk[pl][0] = __byte_perm(t.x, t.y, 0x6420); qk[pl][1] = __byte_perm(t.x, t.y, 0x7531);
+            qk[pl][2] = __byte_perm(t.z, t.w, 0x6420); qk[pl][3] = __byte_perm(t.z, t.w, 0x7531);
+            // nibbles are used unsigned (code + 8): start the accumulator at -8 * sum(q digits)
+            kinit[pl] = -8 * (dp4a_ss(0x01010101u, t.x, 0) + dp4a_ss(0x01010101u, t.y, 0) + dp4a_ss(0x01010101u, t.z, 0) +
+                              dp4a_ss(0x01010101u, t.w, 0));
+        }
+    }
+
+    int iacc[8][3];
+    float facc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) { facc[d] = 0.f; iacc[d][0] = iacc[d][1] = iacc[d][2] = 0; }
+    float m_run = -INFINITY, l_run = 0.f;
+    auto flush = [&](float a) {  // int32 accumulators -> fp32, then move to the new reference
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const float v = fmaf((float)iacc[d][2], 65536.f, fmaf((float)iacc[d][1], 256.f, (float)iacc[d][0]));
+            facc[d] = fmaf(v, dw, facc[d]) * a;
+            iacc[d][0] = iacc[d][1] = iacc[d][2] = 0;
+        }
+    };
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % S;
+        if (tid == 0 && it + PD < n_tiles) {
+            const int nt = it + PD;  // goes into the stage tile nt - S used: every warp must have left it
+            if (nt >= S) { while (!mbar_try_wait(&empty[nt % S], ((nt / S) - 1) & 1)) {} }
+            issue(nt);
+        }
+        const int t0 = t_begin + it * kTile;
+        const int rows = min(kTile, t_end - t0);
+        const bool valid = my_row < rows;
+        const float ks = valid ? __ldg(P.k_scale + t0 + my_row) : 0.f;
+        const float vs = valid ? __ldg(P.v_scale + t0 + my_row) : 0.f;
+        while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
+        const uint8_t* sb = smem_raw + s * C::kStage;
+
+        // ---- K phase: RTT rows per lane, 12 DP4A each; reduce-scatter over the LPR lanes of a row group
+        float dsum[RTT];
+#pragma unroll
+        for (int j = 0; j < RTT; ++j) {
+            const int row = warp * WR + (j ^ swzp) * RPP + kr;
+            int a0 = kinit[0], a1 = kinit[1], a2 = kinit[2];
+            if (KBITS == 8) {
+                const uint4 kw = *reinterpret_cast<const uint4*>(sb + row * C::kKRow + kc * 16);
+                const uint32_t w[4] = {kw.x, kw.y, kw.z, kw.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a0 = dp4a_ss(w[i], qk[0][i], a0); a1 = dp4a_ss(w[i], qk[1][i], a1); a2 = dp4a_ss(w[i], qk[2][i], a2); }
+            } else {
+                const uint2 kw = *reinterpret_cast<const uint2*>(sb + row * C::kKRow + kc * 8);
+                const uint32_t w[4] = {(kw.x >> 4) & 0x0f0f0f0fu, kw.x & 0x0f0f0f0fu, (kw.y >> 4) & 0x0f0f0f0fu, kw.y & 0x0f0f0f0fu};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a0 = dp4a_us(w[i], qk[0][i], a0); a1 = dp4a_us(w[i], qk[1][i], a1); a2 = dp4a_us(w[i], qk[2][i], a2); }
+            }
+            dsum[j] = fmaf((float)a2, 65536.f, fmaf((float)a1, 256.f, (float)a0));
+        }
+        {
+            int n = RTT;
+#pragma unroll
+            for (int o = LPR / 2; o >= 1; o >>= 1) {
+                if (n > 1) {
+                    n >>= 1;
+#pragma unroll
+                    for (int j = 0; j < RTT / 2; ++j)
+                        if (j < n) dsum[j] += __shfl_xor_sync(0xffffffffu, dsum[j + n], o);
+                } else {
+                    dsum[0] += __shfl_xor_sync(0xffffffffu, dsum[0], o);
+                }
+            }
+        }
+        // ---- softmax: one token per lane pair; warp max by REDUX; lazy reference
+        const float sv = valid ? dsum[0] * (dq * ks) : -INFINITY;
+        const float mt = __int_as_float(float_order_key(__int_as_float(__reduce_max_sync(0xffffffffu, float_order_key(sv)))));
+        const bool up = mt > m_run + kMhaLazyLog2;  // warp-uniform; false when every row of the warp is masked
+        if (up) {
+            flush(m_run == -INFINITY ? 0.f : exp2f(m_run - mt));
+            l_run *= m_run == -INFINITY ? 0.f : exp2f(m_run - mt);
+            m_run = mt;
+        } else if ((it & 1023) == 1023) {
+            flush(1.f);  // bound the int32 accumulators on very long splits
+        }
+        const float pw = valid ? exp2f(sv - m_run) : 0.f;
+        if (s_writer) {
+            l_run += pw;
+            const uint32_t W = (uint32_t)__float2int_rn(pw * vs * inv_dw);
+            const int tok = swzp * RPP + kr;  // token of the warp's 16
+            wq_w[tok] = (uint8_t)(W & 255u); wq_w[16 + tok] = (uint8_t)((W >> 8) & 255u); wq_w[32 + tok] = (uint8_t)(W >> 16);
+        }
+        __syncwarp();
+
+        // ---- V phase: byte-transpose four tokens' words, one DP4A per (channel, weight plane)
+#pragma unroll
+        for (int gi = 0; gi < GPH; ++gi) {
+            const int g = hw * GPH + gi;  // tokens 4g .. 4g + 3 of the warp's 16
+            uint32_t wd[3];
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) wd[pl] = *reinterpret_cast<const uint32_t*>(wq_w + pl * 16 + 4 * g);
+            uint32_t lo[4], hi[4];  // INT8: lo = channels 0..3, hi = channels 4..7 (signed bytes); INT4: odd / even channels
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint8_t* src = sb + C::kKTile + (warp * WR + 4 * g + i) * C::kVRow + vc * VB;
+                if (VBITS == 8) { const uint2 t = *reinterpret_cast<const uint2*>(src); lo[i] = t.x; hi[i] = t.y; }
+                else {
+                    const uint32_t t = *reinterpret_cast<const uint32_t*>(src);
+                    lo[i] = __vsub4(t & 0x0f0f0f0fu, 0x08080808u);          // elements 1,3,5,7
+                    hi[i] = __vsub4((t >> 4) & 0x0f0f0f0fu, 0x08080808u);   // elements 0,2,4,6
+                }
+            }
+            uint32_t cl[4], ch[4];
+            transpose4x4(lo[0], lo[1], lo[2], lo[3], cl);
+            transpose4x4(hi[0], hi[1], hi[2], hi[3], ch);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                // channel index inside the lane's 8: INT8 -> lo: c4, hi: 4 + c4; INT4 -> lo: 2*c4 + 1, hi: 2*c4
+                const int dl = VBITS == 8 ? c4 : 2 * c4 + 1, dh = VBITS == 8 ? 4 + c4 : 2 * c4;
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    iacc[dl][pl] = dp4a_su(cl[c4], wd[pl], iacc[dl][pl]);
+                    iacc[dh][pl] = dp4a_su(ch[c4], wd[pl], iacc[dh][pl]);
+                }
+            }
+        }
+        __syncwarp();                           // wq_w is rewritten by the next tile
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+    }
+
+    // ---- merge the warps' partials (own reference each) through shared memory; the ring is idle after the barrier
+    flush(1.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, o);
+    if (lane == 0) { m_s[warp] = m_run; l_s[warp] = l_run; }
+    __syncthreads();
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) M = fmaxf(M, m_s[w]);
+    const float fac = m_run == -INFINITY ? 0.f : exp2f(m_run - M);
+    float* red_s = reinterpret_cast<float*>(smem_raw);  // [kWarps * HW][D]
+    {
+        float* dst = red_s + (warp * HW + hw) * D + vc * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(facc[0] * fac, facc[1] * fac, facc[2] * fac, facc[3] * fac);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(facc[4] * fac, facc[5] * fac, facc[6] * fac, facc[7] * fac);
+    }
+    __syncthreads();
+    const int64_t hq = (int64_t)b * P.Hq + h;
+    if (tid < D) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < kWarps * HW; ++r) sum += red_s[r * D + tid];
+        P.ws_acc[(hq * P.n_splits + split) * D + tid] = sum;
+    }
+    if (tid == 0) {
+        float L = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) L += m_s[w] == -INFINITY ? 0.f : l_s[w] * exp2f(m_s[w] - M);
+        P.ws_ml[(hq * P.n_splits + split) * 2] = M;
+        P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = L;
+    }
+}
+
 // Optional exact "current token" (the reference's decode step sees the new token's K/V unquantized:
 // benchmarker.py:473-477 concatenates them inside the model before they are quantized at :486): it is merged here
 // as one more split with m = q.k_cur * scale, l = 1, acc = v_cur.
@@ -1337,6 +1629,21 @@ int launch_dp4a(dim3 grid, cudaStream_t st, const AttnParams& P) {
     return KVQ_OK;
 }
 
+template <int KBITS, int VBITS, int D>
+int launch_mha(dim3 grid, cudaStream_t st, const AttnParams& P) {
+    using C = MhaCfg<KBITS, VBITS, D>;
+    auto kern = decode_attn_mha_kernel<KBITS, VBITS, D>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    KVQ_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        configured_dev = dev;
+    }
+    kern<<<grid, C::NT, C::kSmem, st>>>(P);
+    return KVQ_OK;
+}
+
 template <int KBITS, int VBITS, int G, int D>
 int launch_gqa(dim3 grid, cudaStream_t st, const AttnParams& P) {
     using C = GqaCfg<KBITS, VBITS, G, D>;
@@ -1357,7 +1664,9 @@ template <int KBITS, int VBITS, int G>
 int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
     if constexpr (G == 1) {  // MHA-shape decode: integer-dot variant (KVQ_ATTN_FP32=1 keeps the fp32 TMA variant for A/B runs)
         static const bool fp32_only = getenv("KVQ_ATTN_FP32") != nullptr;
-        if (tma && !fp32_only) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
+        static const bool block_wide = getenv("KVQ_ATTN_DP4A_BLOCK") != nullptr;  // the first DP4A kernel (block-wide softmax), for A/B runs
+        if (tma && !fp32_only && block_wide) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
+        if (tma && !fp32_only) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
     }
     if constexpr (G <= 2) {
         if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
