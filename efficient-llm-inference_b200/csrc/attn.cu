@@ -1690,9 +1690,9 @@ int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool
 }
 
 int choose_splits(int64_t B, int64_t H, int64_t T, int64_t G) {
-    // TMA variant (G <= 2): one wave of 256-thread CTAs at KVQ_ATTN_CTAS_PER_SM per SM; register-staged variant
-    // (G >= 4, 128-thread CTAs): four per SM
-    const int64_t target = (G <= 2 ? (int64_t)KVQ_ATTN_CTAS_PER_SM : (int64_t)KVQ_ATTN_GQA_CTAS_PER_SM) * sm_count();
+    // one wave of 256-thread CTAs at the variant's CTAs per SM
+    const int64_t per_sm = G == 1 ? KVQ_ATTN_MHA_CTAS_PER_SM : G == 2 ? KVQ_ATTN_CTAS_PER_SM : KVQ_ATTN_GQA_CTAS_PER_SM;
+    const int64_t target = per_sm * sm_count();
     int64_t n = (target + B * H - 1) / (B * H);
     const int64_t max_n = (T + 255) / 256;
     if (n > max_n) n = max_n;
