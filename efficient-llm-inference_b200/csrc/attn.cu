@@ -35,7 +35,16 @@ struct AttnParams {
     int tokens_per_split, n_splits;
     float* ws_acc;  // [B, Hq, n_splits, D]
     float* ws_ml;   // [B, Hq, n_splits, 2]
+    // paged store (table != nullptr): k / v are block pools [n_phys][B][H][bs][row], k_scale / v_scale are [n_phys][bs];
+    // logical block i of the sequence lives in physical block table[i]
+    const int32_t* table; int bs, bs_shift; int64_t kBlk, vBlk;
 };
+
+// position of logical token t in the per-token scale arrays
+__device__ __forceinline__ int64_t tok_index(const AttnParams& P, int t) {
+    if (P.table == nullptr) return t;
+    return (int64_t)__ldg(P.table + (t >> P.bs_shift)) * P.bs + (t & (P.bs - 1));
+}
 
 // 4 codes of one 32-bit word -> 4 floats, exact.  INT8: flip the sign bit so the byte is code+128,
 // drop it into the mantissa of 2^23 (PRMT), subtract 2^23+128.
@@ -295,6 +304,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// one thread: arm the stage's mbarrier and start the bulk copies of a tile (rows tokens from t0) of plane (b, h).  Contiguous
+// store: one copy per tensor.  Paged store: one copy per tensor per block piece, source address through the block table.
+template <int KROW, int VROW, int KTILE>
+__device__ __forceinline__ void issue_tile(const AttnParams& P, int b, int h, int t0, int rows, uint8_t* sb, uint64_t* bar) {
+    mbar_expect_tx(bar, (uint32_t)rows * (KROW + VROW));
+    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+    if (P.table == nullptr) {
+        bulk_g2s(sb, kplane + (int64_t)t0 * KROW, (uint32_t)rows * KROW, bar);
+        bulk_g2s(sb + KTILE, vplane + (int64_t)t0 * VROW, (uint32_t)rows * VROW, bar);
+        return;
+    }
+    for (int r0 = 0; r0 < rows;) {
+        const int t = t0 + r0, w = t & (P.bs - 1);
+        const int len = min(P.bs - w, rows - r0);
+        const int64_t phys = __ldg(P.table + (t >> P.bs_shift));
+        bulk_g2s(sb + r0 * KROW, kplane + phys * P.kBlk + (int64_t)w * KROW, (uint32_t)len * KROW, bar);
+        bulk_g2s(sb + KTILE + r0 * VROW, vplane + phys * P.vBlk + (int64_t)w * VROW, (uint32_t)len * VROW, bar);
+        r0 += len;
+    }
 }
 
 template <int KBITS, int VBITS, int G, int D> struct TmaCfg {
@@ -959,8 +990,6 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     const int t_begin = split * P.tokens_per_split;
     const int t_end = min(P.T, t_begin + P.tokens_per_split);
     const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
-    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
-    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
 
     if (tid == 0) {
 #pragma unroll
@@ -977,12 +1006,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     auto issue = [&](int tile_idx) {
         const int s = tile_idx % S;
         const int t0 = t_begin + tile_idx * kTile;
-        const int rows = min(kTile, t_end - t0);
-        uint8_t* sb = smem_raw + s * C::kStage;
-        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
-        mbar_expect_tx(&full[s], kb + vb);
-        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
-        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+        issue_tile<C::kKRow, C::kVRow, C::kKTile>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
     };
     if (tid == 0) {
         for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
@@ -1033,8 +1057,9 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
 #pragma unroll
         for (int r = 0; r < RTT; ++r) {
             const int row = warp * WR + r * RPP + kr;
-            ksr[r] = row < rows ? __ldg(P.k_scale + t0 + row) : 0.f;
-            vsr[r] = row < rows ? __ldg(P.v_scale + t0 + row) : 0.f;
+            const int64_t ti = row < rows ? tok_index(P, t0 + row) : 0;
+            ksr[r] = row < rows ? __ldg(P.k_scale + ti) : 0.f;
+            vsr[r] = row < rows ? __ldg(P.v_scale + ti) : 0.f;
         }
         while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
         const uint8_t* sb = smem_raw + s * C::kStage;
@@ -1299,8 +1324,6 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     const int t_begin = split * P.tokens_per_split;
     const int t_end = min(P.T, t_begin + P.tokens_per_split);
     const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
-    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
-    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
 
     if (tid == 0) {
 #pragma unroll
@@ -1310,12 +1333,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     auto issue = [&](int tile_idx) {
         const int s = tile_idx % S;
         const int t0 = t_begin + tile_idx * kTile;
-        const int rows = min(kTile, t_end - t0);
-        uint8_t* sb = smem_raw + s * C::kStage;
-        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
-        mbar_expect_tx(&full[s], kb + vb);
-        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
-        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
+        issue_tile<C::kKRow, C::kVRow, C::kKTile>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
     };
     __syncthreads();  // barriers initialised before the first bulk copy can complete on them
     if (tid == 0) {
@@ -1329,7 +1347,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     for (int t = t_begin + tid; t < t_end; t += NT * 8) {  // 8 independent loads in flight
         float v8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v8[u] = t + u * NT < t_end ? __ldg(P.v_scale + t + u * NT) : 0.f;
+        for (int u = 0; u < 8; ++u) v8[u] = t + u * NT < t_end ? __ldg(P.v_scale + tok_index(P, t + u * NT)) : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) vmax = fmaxf(vmax, v8[u]);
     }
@@ -1401,8 +1419,9 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
         const int t0 = t_begin + it * kTile;
         const int rows = min(kTile, t_end - t0);
         const bool valid = my_row < rows;
-        const float ks = valid ? __ldg(P.k_scale + t0 + my_row) : 0.f;
-        const float vs = valid ? __ldg(P.v_scale + t0 + my_row) : 0.f;
+        const int64_t ti = valid ? tok_index(P, t0 + my_row) : 0;
+        const float ks = valid ? __ldg(P.k_scale + ti) : 0.f;
+        const float vs = valid ? __ldg(P.v_scale + ti) : 0.f;
         while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
         const uint8_t* sb = smem_raw + s * C::kStage;
 
@@ -1665,14 +1684,15 @@ int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tm
     if constexpr (G == 1) {  // MHA-shape decode: integer-dot variant (KVQ_ATTN_FP32=1 keeps the fp32 TMA variant for A/B runs)
         static const bool fp32_only = getenv("KVQ_ATTN_FP32") != nullptr;
         static const bool block_wide = getenv("KVQ_ATTN_DP4A_BLOCK") != nullptr;  // the first DP4A kernel (block-wide softmax), for A/B runs
-        if (tma && !fp32_only && block_wide) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
-        if (tma && !fp32_only) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
+        const bool paged = P.table != nullptr;  // only the per-warp kernels read through a block table
+        if (tma && !fp32_only && block_wide && !paged) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
+        if (tma && (!fp32_only || paged)) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
     }
     if constexpr (G <= 2) {
         if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
     } else {  // GQA groups of 4 / 8 are FFMA-bound: register-tiled variant (KVQ_ATTN_GQA_OLD=1 keeps the first version for A/B runs)
         static const bool old_gqa = getenv("KVQ_ATTN_GQA_OLD") != nullptr;
-        if (tma && !old_gqa) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
+        if (tma && (!old_gqa || P.table != nullptr)) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
     }
     if (D == 128) decode_attn_split_kernel<KBITS, VBITS, G, 128><<<grid, kThreads, 0, st>>>(P);
     else decode_attn_split_kernel<KBITS, VBITS, G, 64><<<grid, kThreads, 0, st>>>(P);
@@ -1720,6 +1740,42 @@ extern "C" int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, 
                               sm_scale, nullptr, nullptr, out, out_dtype, workspace, n_splits, stream);
 }
 
+namespace {
+// common tail of the contiguous and paged entry points: split geometry, kernel choice, merge
+int run_decode_attn(AttnParams& P, int k_bits, int v_bits, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                    const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits, bool tma,
+                    cudaStream_t st) {
+    P.B = (int)B; P.Hq = (int)Hq; P.H = (int)H; P.T = (int)T;
+    P.qk_scale_log2 = sm_scale * 1.4426950408889634f;
+    int64_t tps = (T + n_splits - 1) / n_splits;
+    tps = (tps + kTile - 1) / kTile * kTile;
+    P.tokens_per_split = (int)tps;
+    n_splits = (int)((T + tps - 1) / tps);  // splits that actually contain tokens
+    P.n_splits = n_splits;
+    P.ws_acc = (float*)workspace;
+    P.ws_ml = P.ws_acc + B * Hq * (int64_t)n_splits * D;
+    const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
+    const int G = (int)(Hq / H);
+    int rc;
+    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
+    else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P, tma);
+    else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P, tma);
+    else rc = launch_g<4, 8>(G, (int)D, grid, st, P, tma);
+    if (rc != KVQ_OK) return rc;
+    rc = check_launch("decode_attn_split");
+    if (rc != KVQ_OK) return rc;
+    const unsigned mt = (unsigned)D;
+    const CurToken cur{P.q, k_cur, v_cur, P.q_dtype, G, P.qk_scale_log2};
+    switch (out_dtype) {
+        case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
+        case KVQ_F16: rc = launch_merge<KVQ_F16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
+        default: rc = launch_merge<KVQ_BF16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
+    }
+    if (rc != KVQ_OK) return rc;
+    return check_launch("decode_attn_merge");
+}
+}  // namespace
+
 extern "C" int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
                                   const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
                                   const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
@@ -1739,41 +1795,52 @@ extern "C" int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_code
         return reinterpret_cast<uintptr_t>(p) % a == 0 && s.sB % a == 0 && s.sH % a == 0 && s.sT % a == 0;
     };
     KVQ_REQUIRE(al(k_codes, ks, 16) && al(v_codes, vs, 16), "decode_attn: code tensors must be 16-byte aligned with 16-byte-multiple strides");
-    cudaStream_t st = (cudaStream_t)stream;
     AttnParams P{};
     P.q = q; P.q_dtype = q_dtype;
     P.k = (const uint8_t*)k_codes; P.kB = ks.sB; P.kH = ks.sH; P.kT = ks.sT; P.k_scale = k_scale;
     P.v = (const uint8_t*)v_codes; P.vB = vs.sB; P.vH = vs.sH; P.vT = vs.sT; P.v_scale = v_scale;
-    P.B = (int)B; P.Hq = (int)Hq; P.H = (int)H; P.T = (int)T;
-    P.qk_scale_log2 = sm_scale * 1.4426950408889634f;
-    int64_t tps = (T + n_splits - 1) / n_splits;
-    tps = (tps + kTile - 1) / kTile * kTile;
-    P.tokens_per_split = (int)tps;
-    n_splits = (int)((T + tps - 1) / tps);  // splits that actually contain tokens
-    P.n_splits = n_splits;
-    P.ws_acc = (float*)workspace;
-    P.ws_ml = P.ws_acc + B * Hq * (int64_t)n_splits * D;
-    const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
-    const int G = (int)(Hq / H);
-    int rc;
     // the bulk-copy pipeline needs each plane's rows back to back (true for the cache store);
     // KVQ_ATTN_NO_TMA=1 forces the register-staged variant (A/B measurements)
     static const bool no_tma = getenv("KVQ_ATTN_NO_TMA") != nullptr;
     const bool tma = !no_tma && ks.sT == kw && vs.sT == vw;  // (scales are read with plain loads: no alignment demand)
-    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
-    else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P, tma);
-    else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P, tma);
-    else rc = launch_g<4, 8>(G, (int)D, grid, st, P, tma);
-    if (rc != KVQ_OK) return rc;
-    rc = check_launch("decode_attn_split");
-    if (rc != KVQ_OK) return rc;
-    const unsigned mt = (unsigned)D;
-    const CurToken cur{q, k_cur, v_cur, q_dtype, G, P.qk_scale_log2};
-    switch (out_dtype) {
-        case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
-        case KVQ_F16: rc = launch_merge<KVQ_F16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
-        default: rc = launch_merge<KVQ_BF16>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
-    }
-    if (rc != KVQ_OK) return rc;
-    return check_launch("decode_attn_merge");
+    return run_decode_attn(P, k_bits, v_bits, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, tma,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
+                                     const float* k_scale_pool, const void* v_pool, int v_bits, const int64_t v_pool_stride3[3],
+                                     const float* v_scale_pool, const int32_t* block_table, int64_t block_size, int64_t B,
+                                     int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur,
+                                     const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
+                                     kvq_stream_t stream) {
+    KVQ_REQUIRE((k_cur == nullptr) == (v_cur == nullptr), "k_cur and v_cur must be given together");
+    KVQ_REQUIRE(q && k_pool && v_pool && k_scale_pool && v_scale_pool && block_table && out && workspace, "null pointer");
+    KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
+    KVQ_REQUIRE((k_bits == 8 || k_bits == 4) && (v_bits == 8 || v_bits == 4), "k_bits / v_bits must be 8 or 4");
+    KVQ_REQUIRE(D == 64 || D == 128, "decode_attn_paged: head_dim must be 64 or 128 (got %lld)", (long long)D);
+    KVQ_REQUIRE(B >= 1 && H >= 1 && Hq >= 1 && T >= 1 && T <= 0x7fffffff && B <= 65535 && H <= 65535, "bad shape");
+    KVQ_REQUIRE(Hq % H == 0, "Hq must be a multiple of H");
+    const int64_t G = Hq / H;
+    KVQ_REQUIRE(G == 1 || G == 4 || G == 8, "decode_attn_paged: Hq/H must be 1, 4 or 8 (got %lld)", (long long)G);
+    KVQ_REQUIRE(block_size >= 16 && (block_size & (block_size - 1)) == 0, "decode_attn_paged: block_size must be a power of two >= 16 (got %lld)",
+                (long long)block_size);
+    KVQ_REQUIRE(n_splits >= 1, "n_splits must be >= 1");
+    const int64_t kw = k_bits == 8 ? D : D / 2, vw = v_bits == 8 ? D : D / 2;
+    // pool strides in bytes: {physical block, batch, head}; rows of a (block, b, h) are back to back
+    int64_t ks[3] = {B * H * block_size * kw, H * block_size * kw, block_size * kw};
+    int64_t vs[3] = {B * H * block_size * vw, H * block_size * vw, block_size * vw};
+    if (k_pool_stride3) { ks[0] = k_pool_stride3[0]; ks[1] = k_pool_stride3[1]; ks[2] = k_pool_stride3[2]; }
+    if (v_pool_stride3) { vs[0] = v_pool_stride3[0]; vs[1] = v_pool_stride3[1]; vs[2] = v_pool_stride3[2]; }
+    auto al16 = [](const void* p, const int64_t* s) { return reinterpret_cast<uintptr_t>(p) % 16 == 0 && s[0] % 16 == 0 && s[1] % 16 == 0 && s[2] % 16 == 0; };
+    KVQ_REQUIRE(al16(k_pool, ks) && al16(v_pool, vs), "decode_attn_paged: pools must be 16-byte aligned with 16-byte-multiple strides");
+    AttnParams P{};
+    P.q = q; P.q_dtype = q_dtype;
+    P.k = (const uint8_t*)k_pool; P.kBlk = ks[0]; P.kB = ks[1]; P.kH = ks[2]; P.kT = kw; P.k_scale = k_scale_pool;
+    P.v = (const uint8_t*)v_pool; P.vBlk = vs[0]; P.vB = vs[1]; P.vH = vs[2]; P.vT = vw; P.v_scale = v_scale_pool;
+    P.table = block_table; P.bs = (int)block_size;
+    int sh = 0;
+    while ((1LL << sh) < block_size) ++sh;
+    P.bs_shift = sh;
+    return run_decode_attn(P, k_bits, v_bits, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, true,
+                           (cudaStream_t)stream);
 }

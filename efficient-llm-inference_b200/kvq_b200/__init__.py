@@ -25,7 +25,8 @@ from .cache import (  # noqa: F401
     trim_kv_sliding_window,
     trim_kv_strided,
 )
-from .attention import decode_attention_quantized  # noqa: F401
+from .attention import decode_attention_paged, decode_attention_quantized  # noqa: F401
+from .cache.paged_quantized import PagedQuantizedLayerKV  # noqa: F401
 from .cuda import build_cuda_extension, get_cuda_extension  # noqa: F401
 from .core import BenchmarkConfig, CacheConfig, Config, QuantizationConfig  # noqa: F401
 

@@ -68,6 +68,8 @@ SIGNATURES = {
                            + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     "kvq_decode_attn": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
                         + [c_f, c_vp, c_int, c_vp, c_int, c_vp]),
+    "kvq_decode_attn_paged": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp] + [c_i64] * 6
+                              + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -67,3 +67,59 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
                                            L.stream_ptr(q.device)), "kvq_decode_attn")
         L.count_launch(2)
     return out
+
+
+@torch.no_grad()
+def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: torch.Tensor, k_bits: int,
+                           v_pool: torch.Tensor, v_scale_pool: torch.Tensor, v_bits: int, block_table: torch.Tensor,
+                           seq_len: int, sm_scale: Optional[float] = None, out_dtype: Optional[torch.dtype] = None,
+                           workspace: Optional[torch.Tensor] = None, k_cur: Optional[torch.Tensor] = None,
+                           v_cur: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """decode_attention_quantized over a PAGED store: the kernel walks the block table, nothing is stitched.
+
+    k_pool int8 [n_phys,B,H,block_size,D] (k_bits 8) or uint8 [..., D/2] (k_bits 4), contiguous; k_scale_pool fp32
+    [n_phys, block_size]; v likewise; block_table int32 [>= ceil(seq_len / block_size)] (device): logical -> physical
+    block; seq_len = tokens stored.  G = Hq/H in {1,4,8}; block_size a power of two >= 16.
+    (The reference's PagedKVCache re-concatenates its blocks before every use: implementations.py:83-106.)"""
+    L.require_cuda(q, k_pool, v_pool, k_scale_pool, v_scale_pool, block_table)
+    if q.dim() != 4 or q.size(2) != 1:
+        raise RuntimeError("q must be [B, Hq, 1, D] (one decode token)")
+    B, Hq, _, D = q.shape
+    if k_pool.dim() != 5 or v_pool.dim() != 5 or not k_pool.is_contiguous() or not v_pool.is_contiguous():
+        raise RuntimeError("pools must be contiguous [n_phys, B, H, block_size, row]")
+    H, bs = k_pool.size(2), k_pool.size(3)
+    if k_pool.size(1) != B or v_pool.size(1) != B or v_pool.size(2) != H or v_pool.size(3) != bs:
+        raise RuntimeError("K / V pools do not match q")
+    if k_scale_pool.dtype != torch.float32 or v_scale_pool.dtype != torch.float32:
+        raise RuntimeError("attention reads fp32 scales")
+    if tuple(k_scale_pool.shape) != (k_pool.size(0), bs) or tuple(v_scale_pool.shape) != (v_pool.size(0), bs):
+        raise RuntimeError("scale pools must be [n_phys, block_size]")
+    if block_table.dtype != torch.int32 or block_table.numel() * bs < seq_len or seq_len < 1:
+        raise RuntimeError("block_table must be int32 and cover seq_len tokens")
+    if sm_scale is None:
+        sm_scale = float(D) ** -0.5
+    out_dtype = out_dtype or q.dtype
+    qc = q.contiguous()
+    if (k_cur is None) != (v_cur is None):
+        raise RuntimeError("k_cur and v_cur must be given together")
+    if k_cur is not None:
+        L.require_cuda(k_cur, v_cur)
+        if tuple(k_cur.shape) != (B, H, 1, D) or tuple(v_cur.shape) != (B, H, 1, D):
+            raise RuntimeError("k_cur / v_cur must be [B, H, 1, D]")
+        k_cur, v_cur = k_cur.to(q.dtype).contiguous(), v_cur.to(q.dtype).contiguous()
+    k_scale_pool, v_scale_pool, block_table = k_scale_pool.contiguous(), v_scale_pool.contiguous(), block_table.contiguous()
+    out = torch.empty((B, Hq, 1, D), dtype=out_dtype, device=q.device)
+    with L.device_guard(q):
+        ns = ctypes.c_int(1)
+        nbytes = L.lib().kvq_decode_attn_workspace_bytes(B, Hq, H, seq_len, D, ctypes.byref(ns))
+        if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+            workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=q.device)
+        L.check(L.lib().kvq_decode_attn_paged(qc.data_ptr(), L.dtype_code(q.dtype), k_pool.data_ptr(), int(k_bits), None,
+                                              k_scale_pool.data_ptr(), v_pool.data_ptr(), int(v_bits), None,
+                                              v_scale_pool.data_ptr(), block_table.data_ptr(), int(bs), B, Hq, H, int(seq_len), D,
+                                              float(sm_scale), k_cur.data_ptr() if k_cur is not None else None,
+                                              v_cur.data_ptr() if v_cur is not None else None, out.data_ptr(),
+                                              L.dtype_code(out_dtype), workspace.data_ptr(), ns.value, L.stream_ptr(q.device)),
+                "kvq_decode_attn_paged")
+        L.count_launch(2)
+    return out

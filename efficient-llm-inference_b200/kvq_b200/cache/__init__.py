@@ -1,5 +1,6 @@
 """Cache strategies API (reference: src/cache/__init__.py:13-21)."""
 
+from .paged_quantized import PagedQuantizedLayerKV
 from .implementations import (
     PagedKVCache,
     chunk_summarize_kv,
@@ -14,6 +15,7 @@ from .implementations import (
 
 __all__ = [
     "PagedKVCache",
+    "PagedQuantizedLayerKV",
     "trim_kv_sliding_window",
     "chunk_summarize_kv",
     "trim_kv_prefix_window",

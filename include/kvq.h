@@ -253,6 +253,22 @@ KVQ_API int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, 
                                const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
                                kvq_stream_t stream);
 
+/* Same, over a PAGED quantized store (the reference's PagedKVCache only simulates paging and re-stitches the
+ * blocks with torch.cat before every use, src/cache/implementations.py:83-106): the kernel reads K/V blocks through the
+ * block table, no stitch copy.
+ *   k_pool / v_pool     : code pools [n_phys][B][H][block_size][D*bits/8]; *_pool_stride3 = byte strides {block, batch, head}
+ *                         (NULL: contiguous); the rows of one (block, b, h) are back to back
+ *   k/v_scale_pool      : float [n_phys][block_size], one scale per token
+ *   block_table         : device int32 [ceil(T / block_size)]: logical block -> physical block
+ *   block_size          : power of two >= 16
+ * Hq / H in {1, 4, 8}.  Workspace / n_splits as for kvq_decode_attn.  Results are bit-identical to kvq_decode_attn_ex on the
+ * same tokens stored contiguously. */
+KVQ_API int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
+                          const float* k_scale_pool, const void* v_pool, int v_bits, const int64_t v_pool_stride3[3],
+                          const float* v_scale_pool, const int32_t* block_table, int64_t block_size, int64_t B, int64_t Hq,
+                          int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur, const void* v_cur, void* out,
+                          int out_dtype, void* workspace, int n_splits, kvq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
