@@ -41,8 +41,8 @@ struct AttnParams {
 };
 
 // position of logical token t in the per-token scale arrays
-__device__ __forceinline__ int64_t tok_index(const AttnParams& P, int t) {
-    if (P.table == nullptr) return t;
+template <bool PAGED> __device__ __forceinline__ int64_t tok_index(const AttnParams& P, int t) {
+    if constexpr (!PAGED) return t;
     return (int64_t)__ldg(P.table + (t >> P.bs_shift)) * P.bs + (t & (P.bs - 1));
 }
 
@@ -308,24 +308,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // one thread: arm the stage's mbarrier and start the bulk copies of a tile (rows tokens from t0) of plane (b, h).  Contiguous
 // store: one copy per tensor.  Paged store: one copy per tensor per block piece, source address through the block table.
-template <int KROW, int VROW, int KTILE>
+template <int KROW, int VROW, int KTILE, bool PAGED>
 __device__ __forceinline__ void issue_tile(const AttnParams& P, int b, int h, int t0, int rows, uint8_t* sb, uint64_t* bar) {
     mbar_expect_tx(bar, (uint32_t)rows * (KROW + VROW));
     const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
     const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
-    if (P.table == nullptr) {
+    if constexpr (!PAGED) {
         bulk_g2s(sb, kplane + (int64_t)t0 * KROW, (uint32_t)rows * KROW, bar);
         bulk_g2s(sb + KTILE, vplane + (int64_t)t0 * VROW, (uint32_t)rows * VROW, bar);
         return;
     }
-    for (int r0 = 0; r0 < rows;) {
-        const int t = t0 + r0, w = t & (P.bs - 1);
-        const int len = min(P.bs - w, rows - r0);
-        const int64_t phys = __ldg(P.table + (t >> P.bs_shift));
-        bulk_g2s(sb + r0 * KROW, kplane + phys * P.kBlk + (int64_t)w * KROW, (uint32_t)len * KROW, bar);
-        bulk_g2s(sb + KTILE + r0 * VROW, vplane + phys * P.vBlk + (int64_t)w * VROW, (uint32_t)len * VROW, bar);
-        r0 += len;
+    // t0 is a multiple of the 128-token tile and block_size a power of two: a tile is one piece of a large block, or
+    // 128 / block_size whole blocks.  All table entries are loaded before the first copy is issued (one latency, not eight),
+    // and the entries of the next tile are pulled into L1 for the next call.
+    const int blk0 = t0 >> P.bs_shift;
+    if (P.bs >= kTile) {
+        const int64_t phys = __ldg(P.table + blk0);
+        const int w = t0 & (P.bs - 1);
+        bulk_g2s(sb, kplane + phys * P.kBlk + (int64_t)w * KROW, (uint32_t)rows * KROW, bar);
+        bulk_g2s(sb + KTILE, vplane + phys * P.vBlk + (int64_t)w * VROW, (uint32_t)rows * VROW, bar);
+    } else {
+        const int np = (rows + P.bs - 1) >> P.bs_shift;
+        int phys[kTile / 16];
+#pragma unroll
+        for (int i = 0; i < kTile / 16; ++i) phys[i] = i < np ? __ldg(P.table + blk0 + i) : 0;
+#pragma unroll
+        for (int i = 0; i < kTile / 16; ++i) {
+            if (i < np) {
+                const int r0 = i << P.bs_shift, len = min(P.bs, rows - r0);
+                bulk_g2s(sb + r0 * KROW, kplane + (int64_t)phys[i] * P.kBlk, (uint32_t)len * KROW, bar);
+                bulk_g2s(sb + KTILE + r0 * VROW, vplane + (int64_t)phys[i] * P.vBlk, (uint32_t)len * VROW, bar);
+            }
+        }
     }
+    if (t0 + kTile < P.T) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.table + ((t0 + kTile) >> P.bs_shift)));
 }
 
 template <int KBITS, int VBITS, int G, int D> struct TmaCfg {
@@ -961,7 +977,7 @@ template <int BITS> __device__ __forceinline__ void cvt4(const uint32_t* w, int 
     }
 }
 
-template <int KBITS, int VBITS, int G, int D>
+template <int KBITS, int VBITS, int G, int D, bool PAGED>
 __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_attn_gqa_kernel(AttnParams P) {
     using C = GqaCfg<KBITS, VBITS, G, D>;
     constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR;
@@ -1006,7 +1022,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     auto issue = [&](int tile_idx) {
         const int s = tile_idx % S;
         const int t0 = t_begin + tile_idx * kTile;
-        issue_tile<C::kKRow, C::kVRow, C::kKTile>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
+        issue_tile<C::kKRow, C::kVRow, C::kKTile, PAGED>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
     };
     if (tid == 0) {
         for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
@@ -1057,7 +1073,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
 #pragma unroll
         for (int r = 0; r < RTT; ++r) {
             const int row = warp * WR + r * RPP + kr;
-            const int64_t ti = row < rows ? tok_index(P, t0 + row) : 0;
+            const int64_t ti = row < rows ? tok_index<PAGED>(P, t0 + row) : 0;
             ksr[r] = row < rows ? __ldg(P.k_scale + ti) : 0.f;
             vsr[r] = row < rows ? __ldg(P.v_scale + ti) : 0.f;
         }
@@ -1300,7 +1316,7 @@ template <int KBITS, int VBITS, int D> struct MhaCfg {
     static constexpr int kSmem = kBuf + kWarps * 48 + 3 * D + 2 * kWarps * 4 + 2 * kWarps * 4 + 2 * kStages * 8 + 32;
 };
 
-template <int KBITS, int VBITS, int D>
+template <int KBITS, int VBITS, int D, bool PAGED>
 __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_attn_mha_kernel(AttnParams P) {
     using C = MhaCfg<KBITS, VBITS, D>;
     constexpr int NT = C::NT, kWarps = C::kWarps, WR = C::WR;
@@ -1333,7 +1349,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     auto issue = [&](int tile_idx) {
         const int s = tile_idx % S;
         const int t0 = t_begin + tile_idx * kTile;
-        issue_tile<C::kKRow, C::kVRow, C::kKTile>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
+        issue_tile<C::kKRow, C::kVRow, C::kKTile, PAGED>(P, b, h, t0, min(kTile, t_end - t0), smem_raw + s * C::kStage, &full[s]);
     };
     __syncthreads();  // barriers initialised before the first bulk copy can complete on them
     if (tid == 0) {
@@ -1347,7 +1363,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     for (int t = t_begin + tid; t < t_end; t += NT * 8) {  // 8 independent loads in flight
         float v8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v8[u] = t + u * NT < t_end ? __ldg(P.v_scale + tok_index(P, t + u * NT)) : 0.f;
+        for (int u = 0; u < 8; ++u) v8[u] = t + u * NT < t_end ? __ldg(P.v_scale + tok_index<PAGED>(P, t + u * NT)) : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) vmax = fmaxf(vmax, v8[u]);
     }
@@ -1419,7 +1435,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
         const int t0 = t_begin + it * kTile;
         const int rows = min(kTile, t_end - t0);
         const bool valid = my_row < rows;
-        const int64_t ti = valid ? tok_index(P, t0 + my_row) : 0;
+        const int64_t ti = valid ? tok_index<PAGED>(P, t0 + my_row) : 0;
         const float ks = valid ? __ldg(P.k_scale + ti) : 0.f;
         const float vs = valid ? __ldg(P.v_scale + ti) : 0.f;
         while (!mbar_try_wait(&full[s], (it / S) & 1)) {}
@@ -1651,15 +1667,18 @@ int launch_dp4a(dim3 grid, cudaStream_t st, const AttnParams& P) {
 template <int KBITS, int VBITS, int D>
 int launch_mha(dim3 grid, cudaStream_t st, const AttnParams& P) {
     using C = MhaCfg<KBITS, VBITS, D>;
-    auto kern = decode_attn_mha_kernel<KBITS, VBITS, D>;
+    auto kern = decode_attn_mha_kernel<KBITS, VBITS, D, false>;
+    auto kern_paged = decode_attn_mha_kernel<KBITS, VBITS, D, true>;
     static thread_local int configured_dev = -1;
     int dev = 0;
     KVQ_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
         KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        KVQ_CUDA(cudaFuncSetAttribute(kern_paged, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         configured_dev = dev;
     }
-    kern<<<grid, C::NT, C::kSmem, st>>>(P);
+    if (P.table) kern_paged<<<grid, C::NT, C::kSmem, st>>>(P);
+    else kern<<<grid, C::NT, C::kSmem, st>>>(P);
     return KVQ_OK;
 }
 
@@ -1667,15 +1686,18 @@ template <int KBITS, int VBITS, int G, int D>
 int launch_gqa(dim3 grid, cudaStream_t st, const AttnParams& P) {
     using C = GqaCfg<KBITS, VBITS, G, D>;
     constexpr int NT = C::NT;
-    auto kern = decode_attn_gqa_kernel<KBITS, VBITS, G, D>;
+    auto kern = decode_attn_gqa_kernel<KBITS, VBITS, G, D, false>;
+    auto kern_paged = decode_attn_gqa_kernel<KBITS, VBITS, G, D, true>;
     static thread_local int configured_dev = -1;
     int dev = 0;
     KVQ_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
         KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        KVQ_CUDA(cudaFuncSetAttribute(kern_paged, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         configured_dev = dev;
     }
-    kern<<<grid, NT, C::kSmem, st>>>(P);
+    if (P.table) kern_paged<<<grid, NT, C::kSmem, st>>>(P);
+    else kern<<<grid, NT, C::kSmem, st>>>(P);
     return KVQ_OK;
 }
 

@@ -176,6 +176,24 @@ def main():
                 g = report_graph(f"decode attn {mode} G={G} B8 H1 T65536 D128", nbytes,
                                  lambda i: kvq_b200.decode_attention_quantized(q, kcs[i % nl], ksc, kb, vcs[i % nl], vsc, vb, workspace=ws), nl)
                 del kcs, vcs
+    if "paged" in which:
+        # same C5 shard through a shuffled block table (INT8-K / INT4-V): cost of the indirection per block size
+        Ba, Ha, Ta, Da = 8, 1, 65536, 128
+        for G in [int(x) for x in os.environ.get("MB_ATTN_G", "1,8").split(",")]:
+            for bs in (16, 64, 128):
+                nb = Ta // bs
+                nl = 4
+                kps = [torch.randint(-127, 128, (nb, Ba, Ha, bs, Da), device=dev, dtype=torch.int8) for _ in range(nl)]
+                vps = [torch.randint(0, 255, (nb, Ba, Ha, bs, Da // 2), device=dev, dtype=torch.uint8) for _ in range(nl)]
+                ksp = torch.rand(nb, bs, device=dev) * 0.01 + 0.01
+                vsp = torch.rand(nb, bs, device=dev) * 0.01 + 0.01
+                table = torch.randperm(nb, device=dev).to(torch.int32)
+                q = torch.randn(Ba, Ha * G, 1, Da, device=dev, dtype=torch.bfloat16)
+                nbytes = Ba * Ha * Ta * (Da + Da // 2) + 8 * Ta
+                ws = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+                report_graph(f"paged decode attn mixed G={G} block {bs} B8 H1 T65536 D128", nbytes,
+                             lambda i: kvq_b200.decode_attention_paged(q, kps[i % nl], ksp, 8, vps[i % nl], vsp, 4, table, Ta, workspace=ws), nl)
+                del kps, vps
     print("launches", L.launch_count)
 
 
