@@ -167,7 +167,8 @@ class KVCacheBenchmarker:
 
     @torch.no_grad()
     def generate_with_quantized_kv(self, prompt: str, max_new_tokens: int = 32, mode: str = "int8",
-                                   fused_attention: bool = False, evict: Optional[dict] = None) -> Tuple[str, int, float]:
+                                   fused_attention: bool = False, evict: Optional[dict] = None,
+                                   paged_block_size: Optional[int] = None) -> Tuple[str, int, float]:
         """Decode with the KV cache stored quantized (int8 / int4 / mixed).  Returns (text, n_new, cache MB).
 
         Prompt: one fused absmax+quantize launch per layer tensor (one scale per token).  Each step: one
@@ -177,12 +178,14 @@ class KVCacheBenchmarker:
         `KvqFusedCache` and the fused dequant decode-attention kernel instead of dequantizing the whole cache into
         a DynamicCache every step (kvq_b200/hf_cache.py); same cache contents, same per-token scales.
         evict (with fused_attention): a QuantizedLayerKV.evict() keyword dict, e.g. {"strategy": "sliding_window",
-        "window_size": 256}: quantization composed with an eviction strategy in one cache (BASELINE config C2)."""
+        "window_size": 256}: quantization composed with an eviction strategy in one cache (BASELINE config C2).
+        paged_block_size (with fused_attention): keep the codes in a paged pool read through its block table by the
+        attention kernel (quantization composed with paging; a sliding window then drops whole blocks)."""
         ids = self._encode(prompt, False)
         if fused_attention:
-            return self._generate_fused(ids, max_new_tokens, mode, evict)
-        if evict is not None:
-            raise ValueError("a composed quantize + evict cache needs fused_attention=True (KvqFusedCache)")
+            return self._generate_fused(ids, max_new_tokens, mode, evict, paged_block_size)
+        if evict is not None or paged_block_size is not None:
+            raise ValueError("a composed quantize + evict / paged cache needs fused_attention=True (KvqFusedCache)")
         compute_dtype = torch.float16 if str(self.device).startswith("cuda") else torch.float32
         state = {}
 
@@ -201,13 +204,13 @@ class KVCacheBenchmarker:
         return text, n_new, mb(state["q"].estimated_bytes())
 
     @torch.no_grad()
-    def _generate_fused(self, ids: torch.Tensor, max_new_tokens: int, mode: str, evict: Optional[dict] = None
-                        ) -> Tuple[str, int, float]:
+    def _generate_fused(self, ids: torch.Tensor, max_new_tokens: int, mode: str, evict: Optional[dict] = None,
+                        paged_block_size: Optional[int] = None) -> Tuple[str, int, float]:
         from ..hf_cache import KvqFusedCache, fused_attention
         cfg = self.model.config
         n_layers = getattr(cfg, "num_hidden_layers", None) or cfg.n_layer
         dtype = next(self.model.parameters()).dtype
-        cache = KvqFusedCache(n_layers, mode=mode, compute_dtype=dtype, evict=evict)
+        cache = KvqFusedCache(n_layers, mode=mode, compute_dtype=dtype, evict=evict, paged_block_size=paged_block_size)
         with fused_attention(self.model):
             out = self.model(input_ids=ids, use_cache=True, past_key_values=cache)
             logits = out.logits[:, -1, :]
@@ -263,7 +266,8 @@ class KVCacheBenchmarker:
     def benchmark_method(self, prompts: list, method: str = "no_cache", max_new_tokens: int = 32, window_size: int = 256,
                          block_size: int = 64, chunk_size: int = 64, keep_last: int = 256, mode: str = "int8",
                          prefix_len: int = 32, stride: int = 4, keep_per_block: int = 8, old_budget: int = 64,
-                         fused_attention: bool = False, evict: Optional[dict] = None) -> dict:
+                         fused_attention: bool = False, evict: Optional[dict] = None,
+                         paged_block_size: Optional[int] = None) -> dict:
         """Run `method` over `prompts` (sequentially) and report time, tokens/s and memory.
         `fused_attention` (extension, default off) applies to the quant_* methods, see generate_with_quantized_kv."""
         assert method in self.VALID_METHODS, f"Invalid method: {method}"
@@ -272,9 +276,9 @@ class KVCacheBenchmarker:
             "no_cache": lambda p: (self.generate_no_cache(p, max_new_tokens)[1], 0.0),
             "full_cache": lambda p: (self.generate_with_cache(p, max_new_tokens)[1], nan),
             "sliding_window": lambda p: (self.generate_with_sliding_window(p, max_new_tokens, window_size=window_size)[1], nan),
-            "quant_int8": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int8", fused_attention=fused_attention, evict=evict)[1:3],
-            "quant_int4": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int4", fused_attention=fused_attention, evict=evict)[1:3],
-            "quant_mixed": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="mixed", fused_attention=fused_attention, evict=evict)[1:3],
+            "quant_int8": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int8", fused_attention=fused_attention, evict=evict, paged_block_size=paged_block_size)[1:3],
+            "quant_int4": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="int4", fused_attention=fused_attention, evict=evict, paged_block_size=paged_block_size)[1:3],
+            "quant_mixed": lambda p: self.generate_with_quantized_kv(p, max_new_tokens, mode="mixed", fused_attention=fused_attention, evict=evict, paged_block_size=paged_block_size)[1:3],
             "paged_attention": lambda p: self.generate_with_paged_attention(p, max_new_tokens, block_size=block_size)[1:3],
             "chunked_cache": lambda p: self.generate_with_chunked_cache(p, max_new_tokens, chunk_size=chunk_size,
                                                                         keep_last=keep_last)[1:3],

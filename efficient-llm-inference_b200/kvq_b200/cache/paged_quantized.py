@@ -191,14 +191,18 @@ class PagedQuantizedLayerKV:
 
     @torch.no_grad()
     def attend(self, q: torch.Tensor, sm_scale: Optional[float] = None, k_cur: Optional[torch.Tensor] = None,
-               v_cur: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-        """Decode attention of q [B,Hq,1,D] over the stored tokens, read through the block table."""
+               v_cur: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+               seq_len: Optional[int] = None) -> torch.Tensor:
+        """Decode attention of q [B,Hq,1,D] over the stored tokens (or the first seq_len of them), read through the block table."""
         if len(self) == 0:
             raise ValueError("Empty cache")
+        n = len(self) if seq_len is None else int(seq_len)
+        if not 1 <= n <= len(self):
+            raise ValueError(f"seq_len must be in [1, {len(self)}]")
         if self._ws is None:
             self._ws = torch.empty(8 << 20, dtype=torch.float32, device=q.device)
         return decode_attention_paged(q, self._k.codes, self._k.scales_f32, self.k_bits, self._v.codes, self._v.scales_f32,
-                                      self.v_bits, self._k.table, len(self), sm_scale=sm_scale, out_dtype=out_dtype,
+                                      self.v_bits, self._k.table, n, sm_scale=sm_scale, out_dtype=out_dtype,
                                       workspace=self._ws, k_cur=k_cur, v_cur=v_cur)
 
     def allocated_bytes(self) -> int:

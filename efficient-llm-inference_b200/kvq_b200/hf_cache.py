@@ -27,6 +27,7 @@ import torch
 from transformers.cache_utils import Cache, CacheLayerMixin
 
 from .attention import decode_attention_quantized
+from .cache.paged_quantized import PagedQuantizedLayerKV
 from .quantization.ops import QuantizedLayerKV
 
 ATTN_NAME = "kvq_fused"
@@ -40,13 +41,25 @@ class KvqCacheLayer(CacheLayerMixin):
 
     is_sliding = False
 
-    def __init__(self, layer_idx: int, mode: str, compute_dtype: torch.dtype, group=None, evict: Optional[dict] = None):
+    def __init__(self, layer_idx: int, mode: str, compute_dtype: torch.dtype, group=None, evict: Optional[dict] = None,
+                 paged_block_size: Optional[int] = None):
         super().__init__()
         self.layer_idx = layer_idx
         self.mode = mode
         self.evict = evict  # e.g. {"strategy": "sliding_window", "window_size": 256}: applied to the store after every step
-        self.store = QuantizedLayerKV(mode=mode, device="cuda", compute_dtype=compute_dtype, group=group)
+        self.paged_block_size = paged_block_size
+        if paged_block_size is not None:
+            if group is not None:
+                raise ValueError("the paged store is single-GPU (per-token scales of a head shard need the allreduce path)")
+            if evict is not None and evict.get("strategy") != "sliding_window":
+                raise ValueError("the paged store evicts by dropping leading blocks: sliding_window only")
+        self.store = self._new_store(compute_dtype, group)
         self.cached_before_update = 0
+
+    def _new_store(self, compute_dtype, group):
+        if self.paged_block_size is not None:
+            return PagedQuantizedLayerKV(mode=self.mode, block_size=self.paged_block_size, device="cuda", compute_dtype=compute_dtype)
+        return QuantizedLayerKV(mode=self.mode, device="cuda", compute_dtype=compute_dtype, group=group)
 
     def lazy_initialization(self, key_states: torch.Tensor, value_states: torch.Tensor) -> None:
         self.dtype, self.device = key_states.dtype, key_states.device
@@ -59,7 +72,10 @@ class KvqCacheLayer(CacheLayerMixin):
         if self.evict is not None and len(self.store) > 0:
             # trim what earlier steps accumulated (the reference's loops trim after every step, benchmarker.py:199-205):
             # doing it here, before the append, keeps `cached_before_update` tokens contiguous for this step's attention
-            self.store.evict(**self.evict)
+            if self.paged_block_size is not None:
+                self.store.evict_sliding_window(self.evict.get("window_size", 256))  # whole leading blocks: a table edit
+            else:
+                self.store.evict(**self.evict)
         self.cached_before_update = len(self.store)
         self.store.append_tokens(key_states, value_states)  # one scale per token, one launch per tensor
         _pending[self.layer_idx] = self
@@ -82,7 +98,7 @@ class KvqCacheLayer(CacheLayerMixin):
         return None
 
     def reset(self) -> None:
-        self.store = QuantizedLayerKV(mode=self.mode, device="cuda", compute_dtype=self.store.compute_dtype, group=self.store.group)
+        self.store = self._new_store(self.store.compute_dtype, getattr(self.store, "group", None))
 
     def reorder_cache(self, beam_idx):
         raise NotImplementedError("beam search is not supported on the quantized store")
@@ -92,16 +108,19 @@ class KvqFusedCache(Cache):
     """`past_key_values` object backed by quantized stores (modes "int8", "int4", "mixed")."""
 
     def __init__(self, n_layers: int, mode: str = "int8", compute_dtype: torch.dtype = torch.float16, group=None,
-                 evict: Optional[dict] = None):
+                 evict: Optional[dict] = None, paged_block_size: Optional[int] = None):
         """evict (optional): a QuantizedLayerKV.evict() keyword dict, e.g. {"strategy": "sliding_window",
-        "window_size": 256} -- BASELINE config C2's "quant_mixed + sliding_window 256" as ONE cache object."""
+        "window_size": 256} -- BASELINE config C2's "quant_mixed + sliding_window 256" as ONE cache object.
+        paged_block_size (optional): keep the codes in a paged pool (PagedQuantizedLayerKV) read through its block table by
+        the attention kernel; a sliding window then drops whole leading blocks."""
         assert mode in ["int8", "int4", "mixed"], f"Invalid mode: {mode}"
-        super().__init__(layers=[KvqCacheLayer(i, mode, compute_dtype, group, evict) for i in range(n_layers)])
+        super().__init__(layers=[KvqCacheLayer(i, mode, compute_dtype, group, evict, paged_block_size) for i in range(n_layers)])
         self.mode = mode
 
     def estimated_bytes(self) -> int:
-        """Same accounting as QuantizedKVCache.estimated_bytes (reference ops.py:357-363)."""
-        return sum(layer.store.estimated_bytes() for layer in self.layers)
+        """Same accounting as QuantizedKVCache.estimated_bytes (reference ops.py:357-363); blocks in use for a paged store."""
+        return sum(layer.store.allocated_bytes() if layer.paged_block_size is not None else layer.store.estimated_bytes()
+                   for layer in self.layers)
 
     def to_past_key_values(self) -> tuple:
         """Dequantized ((k, v), ...) like QuantizedKVCache.to_past_key_values, for inspection."""
@@ -121,6 +140,9 @@ def kvq_fused_attention(module, query: torch.Tensor, key: torch.Tensor, value: t
         from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
         return ALL_ATTENTION_FUNCTIONS["sdpa"](module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
     T = layer.cached_before_update
+    if layer.paged_block_size is not None:
+        out = layer.store.attend(query, sm_scale=scaling, k_cur=key, v_cur=value, out_dtype=query.dtype, seq_len=T)
+        return out.transpose(1, 2), None
     kc, ks, kb, vc, vs, vb = layer.store.quantized()
     out = decode_attention_quantized(query, kc[:, :, :T], ks[:T], kb, vc[:, :, :T], vs[:T], vb, sm_scale=scaling,
                                      out_dtype=query.dtype, k_cur=key, v_cur=value)

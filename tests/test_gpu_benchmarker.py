@@ -177,3 +177,24 @@ def test_fused_attention_on_a_gqa_model(kv_heads, head_dim):
     assert t_fused[1] == t_plain[1] == 8 and t_fused[2] == t_plain[2]
     agree = sum(x == y for x, y in zip(t_fused[0].split(), t_plain[0].split())) / len(t_plain[0].split())
     assert agree >= 0.95
+
+
+def test_fused_attention_on_a_paged_store(bench):
+    """Quantization composed with paging behind the HF cache interface: same codes, attention bit-identical to the contiguous
+    store, so the generated tokens are identical; with a sliding window the paged store drops whole blocks."""
+    for mode in ("int8", "mixed"):
+        flat = bench.generate_with_quantized_kv(PROMPT, 12, mode=mode, fused_attention=True)
+        paged = bench.generate_with_quantized_kv(PROMPT, 12, mode=mode, fused_attention=True, paged_block_size=16)
+        assert paged[0] == flat[0] and paged[1] == flat[1] == 12
+        assert paged[2] >= flat[2]  # blocks in use, including the unused tail of the last block
+    ev = {"strategy": "sliding_window", "window_size": 32}
+    text, n_new, est_mb = bench.generate_with_quantized_kv(PROMPT, 6, mode="mixed", fused_attention=True, evict=ev, paged_block_size=16)
+    assert n_new == 6
+    # 88 + 6 tokens, window 32, blocks of 16: after the last trim 32..47 cached tokens remain, + the token of the last step
+    assert 3 * (4 * 32 * (64 + 32)) / 1024 ** 2 <= est_mb <= 3 * (4 * 64 * (64 + 32) + 2 * 64 * 2) / 1024 ** 2
+    r = bench.benchmark_method([PROMPT], method="quant_mixed", max_new_tokens=4, fused_attention=True, paged_block_size=32)
+    assert r["total_new_tokens"] == 4 and r["est_kv_cache_mb_avg"] > 0
+    with pytest.raises(ValueError):
+        bench.generate_with_quantized_kv(PROMPT, 2, mode="int8", paged_block_size=16)
+    with pytest.raises(ValueError):
+        bench.generate_with_quantized_kv(PROMPT, 2, mode="int8", fused_attention=True, paged_block_size=16, evict={"strategy": "strided"})
