@@ -587,6 +587,42 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const char* __re
     }
 }
 
+// Per-token scales on a [B,H,T,D] store whose (b,h) planes are T contiguous rows at a uniform plane stride (the
+// QuantizedLayerKV buffer: capacity >= T per plane; get_kv() dequantizes the whole cache every decode step in the reference's
+// loop, ops.py:213-269): the same short-CTA flat stream over the OUTPUT as above -- the strided-row kernel below is a persistent
+// loop and 7-15 % slower on this write-heavy 1:2 / 1:4 stream.  Output vector j -> plane j / vpp, position j % vpp inside the
+// plane (one 64-bit division per chunk, stepped per vector), token = position >> vpr_shift (vectors per row: a power of two).
+template <int ODT, int BITS, bool PK, int UNROLL>
+__global__ void __launch_bounds__(kThreads) dequant_flat_token_kernel(const char* __restrict__ codes, int64_t n_vec,
+                                                                      const void* __restrict__ scale, int scale_dtype,
+                                                                      uint4* __restrict__ out, FlatWork w, int vpr_shift,
+                                                                      int64_t vpp, int64_t plane_stride) {
+    constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
+    int ti; int64_t c0, c1;
+    flat_split(w, ti, c0, c1);
+    for (int64_t c = c0; c < c1; c += w.cstep) {
+        const int64_t base = c * (kThreads * UNROLL);
+        const int64_t plane0 = base / vpp, within0 = base - plane0 * vpp;  // uniform over the CTA
+        Raw<kIn> r[UNROLL];
+        ScaleArg<PK> sv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = base + u * kThreads + threadIdx.x;
+            if (j < n_vec) {
+                int64_t plane = plane0, pos = within0 + u * kThreads + threadIdx.x;
+                while (pos >= vpp) { pos -= vpp; ++plane; }  // a chunk reaches into the next plane(s) only at a plane's end
+                r[u].load(codes + plane * plane_stride + pos * kIn);
+                sv[u].load(scale, scale_dtype, pos >> vpr_shift);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t j = base + u * kThreads + threadIdx.x;
+            if (j < n_vec) dequant_store<ODT, BITS, PK>(r[u], sv[u], out + j);
+        }
+    }
+}
+
 // g.x* describe the CODES (bytes), g.q* the OUTPUT (bytes); vpr = 16-byte OUTPUT vectors per row
 template <int ODT, int BITS, bool PK, int UNROLL>
 __global__ void __launch_bounds__(kThreads) dequant_rows_kernel(const char* __restrict__ codes, RowGeom g,
@@ -832,6 +868,22 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
         } else {
             KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, false, U><<<grid, kThreads, 0, st>>>(
                                            (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w));
+        }
+    } else if (per_token && rows_ok && cs.sT == W && cs.sB == H * cs.sH && ((D * oes / 16) & (D * oes / 16 - 1)) == 0) {
+        // planes of T contiguous rows at a uniform stride (the cache store: capacity >= T): flat stream over the output
+        const int64_t n_vec = n * oes / 16;
+        constexpr int U = 4;
+        FlatWork w; unsigned grid;
+        flat_work(n_vec, U, 2, 1, w, grid);
+        int sh = 0;
+        while ((1 << sh) < D * oes / 16) ++sh;
+        const int64_t vpp = T * (D * oes / 16);
+        if (pk) {
+            if (out_dtype == KVQ_F16) dequant_flat_token_kernel<KVQ_F16, BITS, true, U><<<grid, kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w, sh, vpp, cs.sH);
+            else dequant_flat_token_kernel<KVQ_BF16, BITS, true, U><<<grid, kThreads, 0, st>>>((const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w, sh, vpp, cs.sH);
+        } else {
+            KVQ_DISPATCH_DT(out_dtype, dequant_flat_token_kernel<DT, BITS, false, U><<<grid, kThreads, 0, st>>>(
+                                           (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w, sh, vpp, cs.sH));
         }
     } else if (rows_ok) {
         const int64_t contig[4] = {H * T * D, T * D, D, 1};
