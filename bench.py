@@ -181,7 +181,9 @@ def workload_config(cfg, n_gpus, where):
         "workload": (f"Llama-3-8B-shape synthetic KV (L={cfg['L']} x {{K,V}}, B={cfg['B']}, H={cfg['H']} KV heads, T={cfg['T']}, "
                      f"D={cfg['D']}, bf16): INT4 pack/unpack, per-tensor scale, head-sharded over {n_gpus} GPU(s)"),
         "baseline_config": "BASELINE.json configs[2]",
-        "step": "absmax of all 64 layer tensors (1 launch) -> [allreduce-max] -> quantize+pack (1 launch) -> unpack+dequantize (1 launch)",
+        "step": ("absmax of all 64 layer tensors (1 launch) -> quantize+pack (1 launch) -> unpack+dequantize (1 launch)" if n_gpus == 1 or where != "gpu" else
+                 "absmax (2 launches, 32 layer tensors each) -> allreduce-max of each half, overlapped with the other half's kernel -> "
+                 "quantize+pack (2 launches) -> unpack+dequantize (1 launch)"),
         "algorithmic_bytes_per_element": 7.0,
         "l2_policy": "inputs (64 GiB whole job) are far larger than the 126 MB L2; no flush needed",
         "parallelism": f"kv-head shard x{n_gpus}" if where == "gpu" else "cpu",
@@ -237,13 +239,29 @@ def run_c3(args, cfg):
     stream = L.stream_ptr(dev)
     dom_events = []  # (start, end) around every launch of the dominant kernel inside the timed region
 
+    half = n_tensors // 2
+
     def step(timed: bool):
-        # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between
-        L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
+        # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between.  Head-sharded
+        # (N > 1): the batch goes through absmax / quantize in two halves so that the allreduce of one half (NCCL's stream)
+        # overlaps the other half's kernel -- SURVEY 8e: "overlap by launching phase-1 for tensor i+1 before phase-2 of tensor i"
+        n_launch = 3
         if world > 1 and not os.environ.get("KVQ_BENCH_NO_ALLREDUCE"):  # (env: debugging aid, not a valid bench line)
-            dist.all_reduce(bits, op=dist.ReduceOp.MAX)  # the only collective on the path
-        L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
-                                      scales.data_ptr(), None, stream), "kvq_quant_batched")
+            works = []
+            for lo_t, cnt in ((0, half), (half, n_tensors - half)):
+                L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr() + 8 * lo_t, L.BF16, cnt, n_local, bits.data_ptr() + 4 * lo_t, stream),
+                        "kvq_absmax_batched")
+                works.append(dist.all_reduce(bits[lo_t: lo_t + cnt], op=dist.ReduceOp.MAX, async_op=True))  # the only collective on the path
+            for (lo_t, cnt), wk in zip(((0, half), (half, n_tensors - half)), works):
+                wk.wait()  # stream-level wait
+                L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr() + 8 * lo_t, L.BF16, cnt, n_local, 4 | L.ABSMAX_COVERS_INPUT,
+                                              bits.data_ptr() + 4 * lo_t, 1e-8, tp.ptrs.data_ptr() + 8 * lo_t,
+                                              scales.data_ptr() + 2 * lo_t, None, stream), "kvq_quant_batched")
+            n_launch = 5
+        else:
+            L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
+            L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
+                                          scales.data_ptr(), None, stream), "kvq_quant_batched")
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -252,7 +270,7 @@ def run_c3(args, cfg):
         if timed:
             e1.record()
             dom_events.append((e0, e1))
-        return 3
+        return n_launch
 
     def sync_all():
         if world > 1:

@@ -753,6 +753,10 @@ void flat_work(int64_t n_vec, int unroll, int kind, int64_t n_tensors, FlatWork&
     int64_t bpt, cpc;
     if (mode < 0) {
         bpt = (int64_t)sm_count() * -mode;
+        // small tensors (a head shard at N = 8 is 128 MB): keep ~3 strided chunks per CTA rather than degenerating into one chunk
+        // per CTA, which costs the issue-bound quantize kernel 15-20 % (profiles/r1c_grid_sweep.log, table 2 row cpc = 1)
+        static const int min_cpc = env_int("KVQ_FLAT_MIN_CPC", 3);
+        if (kind != 2 && min_cpc > 1 && bpt * min_cpc > w.chunks) bpt = (w.chunks + min_cpc - 1) / min_cpc;
         if (bpt > w.chunks) bpt = w.chunks;
         if (bpt > max_bpt) bpt = max_bpt;
         if (bpt < 1) bpt = 1;

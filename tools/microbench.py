@@ -80,7 +80,7 @@ def main():
     lib = L.lib()
     st = L.stream_ptr(dev)
     which = sys.argv[1:] or ["copy", "quant", "token", "evict", "chunk", "attn"]
-    B, H, T, D = 16, 8, 32768, 128
+    B, H, T, D = 16, int(os.environ.get("MB_H", "8")), 32768, 128  # MB_H=1: the per-GPU head shard at N = 8 (128 MB tensors)
     N = B * H * T * D
     nbuf = 4
     if "copy" in which:
