@@ -26,7 +26,7 @@ from typing import Optional, Tuple
 import torch
 from transformers.cache_utils import Cache, CacheLayerMixin
 
-from .attention import decode_attention_quantized
+from .attention import decode_attention_quantized  # noqa: F401  (re-exported for users of this module)
 from .cache.paged_quantized import PagedQuantizedLayerKV
 from .quantization.ops import QuantizedLayerKV
 
@@ -143,9 +143,7 @@ def kvq_fused_attention(module, query: torch.Tensor, key: torch.Tensor, value: t
     if layer.paged_block_size is not None:
         out = layer.store.attend(query, sm_scale=scaling, k_cur=key, v_cur=value, out_dtype=query.dtype, seq_len=T)
         return out.transpose(1, 2), None
-    kc, ks, kb, vc, vs, vb = layer.store.quantized()
-    out = decode_attention_quantized(query, kc[:, :, :T], ks[:T], kb, vc[:, :, :T], vs[:T], vb, sm_scale=scaling,
-                                     out_dtype=query.dtype, k_cur=key, v_cur=value)
+    out = layer.store.attend(query, T, key, value, scaling, query.dtype)
     return out.transpose(1, 2), None  # [B, 1, Hq, D], like the stock attention functions
 
 

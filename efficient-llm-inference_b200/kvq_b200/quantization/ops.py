@@ -223,6 +223,9 @@ class _TokenStore:
         self.T = 0
         self.D = 0
         self.n_scale_entries = 0  # how many scale tensors the reference would hold (one per append)
+        self._bits_scratch: Optional[torch.Tensor] = None
+        self._stride3 = None      # ctypes {sB,sH,sT} of `codes`, rebuilt when the buffer is reallocated
+        self._stride3_of = None
 
     # ---- views of the live region
     def live_codes(self) -> torch.Tensor:
@@ -268,18 +271,27 @@ class _TokenStore:
         n = x.size(2)
         self._reserve(x, n)
         lo = self.start + self.T
-        dst = self.codes[:, :, lo: lo + n]
-        sc = self.scales[lo: lo + n]
-        s32 = self.scales_f32[lo: lo + n]
         sh, st = L.shape_stride(x)
         lib, dt, stream = L.lib(), L.dtype_code(x.dtype), L.stream_ptr(x.device)
         if group is None:
-            bits = torch.empty(n, dtype=torch.int32, device=x.device)
-            L.check(lib.kvq_quant_per_token_fused(x.data_ptr(), dt, sh, st, self.bits, float(eps), dst.data_ptr(),
-                                                  L.stride3(dst), sc.data_ptr(), s32.data_ptr(), bits.data_ptr(), stream),
+            # the decode loop comes through here twice per layer per step: destination pointers by arithmetic on the
+            # buffers (rows [lo, lo + n) of every plane), no tensor views
+            codes = self.codes
+            if self._stride3_of is not codes:
+                self._stride3, self._stride3_of = L.stride3(codes), codes
+            bits = self._bits_scratch
+            if bits is None or bits.numel() < n or bits.device != x.device:  # absmax words: scratch, reused across steps
+                bits = self._bits_scratch = torch.empty(max(n, 64), dtype=torch.int32, device=x.device)
+            L.check(lib.kvq_quant_per_token_fused(x.data_ptr(), dt, sh, st, self.bits, float(eps),
+                                                  codes.data_ptr() + lo * codes.stride(2), self._stride3,
+                                                  self.scales.data_ptr() + lo * self.scales.element_size(),
+                                                  self.scales_f32.data_ptr() + 4 * lo, bits.data_ptr(), stream),
                     "kvq_quant_per_token_fused")
             L.count_launch()
         else:
+            dst = self.codes[:, :, lo: lo + n]
+            sc = self.scales[lo: lo + n]
+            s32 = self.scales_f32[lo: lo + n]
             bits = _absmax_bits(x, L.PER_TOKEN, group)
             fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
             L.check(fn(x.data_ptr(), dt, sh, st, L.PER_TOKEN | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), float(eps), dst.data_ptr(),
@@ -374,6 +386,7 @@ class QuantizedLayerKV:
         self.group = group  # torch.distributed group of a head-sharded cache (None: single GPU)
         self._k = _TokenStore(4 if mode == "int4" else 8)
         self._v = _TokenStore(8 if mode == "int8" else 4)
+        self._attn_ws: Optional[torch.Tensor] = None  # split-K workspace of attend()
 
     # --- reference-visible storage, as views of the contiguous store ----------------------------
     @property
@@ -482,6 +495,55 @@ class QuantizedLayerKV:
             raise ValueError("Empty cache")
         return (self._k.live_codes(), self._k.live_scales_f32(), self._k.bits,
                 self._v.live_codes(), self._v.live_scales_f32(), self._v.bits)
+
+    @torch.no_grad()
+    def attend(self, q: torch.Tensor, seq_len: Optional[int] = None, k_cur: Optional[torch.Tensor] = None,
+               v_cur: Optional[torch.Tensor] = None, sm_scale: Optional[float] = None,
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Fused dequant decode attention of q [B,Hq,1,D] over the first seq_len stored tokens (default: all), plus the step's
+        own token k_cur / v_cur [B,H,1,D] exactly.  Same kernel call as decode_attention_quantized(*self.quantized(), ...)
+        without building the views: the per-step path of KvqFusedCache."""
+        import ctypes
+        k, v = self._k, self._v
+        T = k.T if seq_len is None else int(seq_len)
+        if not 1 <= T <= k.T:
+            raise ValueError("Empty cache" if k.T == 0 else f"seq_len must be in [1, {k.T}]")
+        L.require_cuda(q)
+        if q.dim() != 4 or q.size(2) != 1 or q.size(0) != k.codes.size(0) or q.size(3) != k.D:
+            raise RuntimeError("q must be [B, Hq, 1, D] matching the cache")
+        B, Hq, _, D = q.shape
+        H = k.codes.size(1)
+        if (k_cur is None) != (v_cur is None):
+            raise RuntimeError("k_cur and v_cur must be given together")
+        if k_cur is not None:
+            if tuple(k_cur.shape) != (B, H, 1, D) or tuple(v_cur.shape) != (B, H, 1, D):
+                raise RuntimeError("k_cur / v_cur must be [B, H, 1, D]")
+            k_cur, v_cur = k_cur.to(q.dtype).contiguous(), v_cur.to(q.dtype).contiguous()
+        qc = q.contiguous()
+        out_dtype = out_dtype or q.dtype
+        out = torch.empty((B, Hq, 1, D), dtype=out_dtype, device=q.device)
+        for st in (k, v):
+            if st._stride3_of is not st.codes:
+                st._stride3, st._stride3_of = L.stride3(st.codes), st.codes
+        with L.device_guard(q):
+            lib = L.lib()
+            ns = ctypes.c_int(1)
+            nbytes = lib.kvq_decode_attn_workspace_bytes(B, Hq, H, T, D, ctypes.byref(ns))
+            ws = self._attn_ws
+            if ws is None or ws.numel() * 4 < nbytes or ws.device != q.device:
+                ws = self._attn_ws = torch.empty(max(nbytes, 1 << 20) // 4, dtype=torch.float32, device=q.device)
+            L.check(lib.kvq_decode_attn_ex(qc.data_ptr(), L.dtype_code(q.dtype),
+                                           k.codes.data_ptr() + k.start * k.codes.stride(2), k.bits, k._stride3,
+                                           k.scales_f32.data_ptr() + 4 * k.start,
+                                           v.codes.data_ptr() + v.start * v.codes.stride(2), v.bits, v._stride3,
+                                           v.scales_f32.data_ptr() + 4 * v.start, B, Hq, H, T, D,
+                                           float(D) ** -0.5 if sm_scale is None else float(sm_scale),
+                                           k_cur.data_ptr() if k_cur is not None else None,
+                                           v_cur.data_ptr() if v_cur is not None else None, out.data_ptr(),
+                                           L.dtype_code(out_dtype), ws.data_ptr(), ns.value, L.stream_ptr(q.device)),
+                    "kvq_decode_attn")
+            L.count_launch(2)
+        return out
 
     def estimated_bytes(self) -> int:
         """Stored codes + scales, as the reference counts them (ops.py:271-290)."""
