@@ -135,3 +135,31 @@ def test_attention_on_a_slid_store(kvq, oracle):
     before = layer.quantized()[0].clone()
     layer.append_tokens(k[:, :, :400].cuda(), v[:, :, :400].cuda())
     assert len(layer) == 530 and torch.equal(layer.quantized()[0][:, :, :130], before)
+
+
+@pytest.mark.parametrize("mode", ["int8", "mixed"])
+def test_store_attend_is_the_same_kernel_call(kvq, mode):
+    """QuantizedLayerKV.attend (pointer arithmetic on the buffers, the per-step path of KvqFusedCache) == decode_attention_quantized
+    on the views, bit for bit: full length, a prefix (seq_len), after a sliding window moved the live region, with the step's own token."""
+    g = torch.Generator().manual_seed(11)
+    B, H, T, D = 2, 2, 700, 128
+    k, v = torch.randn(B, H, T, D, generator=g).half().cuda(), torch.randn(B, H, T, D, generator=g).half().cuda()
+    q = torch.randn(B, 4 * H, 1, D, generator=g).half().cuda()
+    kc1, vc1 = torch.randn(B, H, 1, D, generator=g).half().cuda(), torch.randn(B, H, 1, D, generator=g).half().cuda()
+    layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float16)
+    layer.append_tokens(k, v)
+    for trim in (None, 300):
+        if trim:
+            layer.evict("sliding_window", window_size=trim)
+        kc, ks, kb, vc, vs, vb = layer.quantized()
+        n = kc.size(2)
+        assert torch.equal(layer.attend(q), kvq.decode_attention_quantized(q, kc, ks, kb, vc, vs, vb))
+        assert torch.equal(layer.attend(q, n - 5, kc1, vc1, 0.11, torch.float32),
+                           kvq.decode_attention_quantized(q, kc[:, :, : n - 5], ks[: n - 5], kb, vc[:, :, : n - 5], vs[: n - 5], vb,
+                                                          sm_scale=0.11, out_dtype=torch.float32, k_cur=kc1, v_cur=vc1))
+    with pytest.raises(ValueError):
+        layer.attend(q, 10 ** 6)
+    with pytest.raises(RuntimeError):
+        layer.attend(q[:, :, :, :64])
+    with pytest.raises(ValueError):
+        kvq.QuantizedLayerKV(mode, "cuda", torch.float16).attend(q)
