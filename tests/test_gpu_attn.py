@@ -163,3 +163,47 @@ def test_store_attend_is_the_same_kernel_call(kvq, mode):
         layer.attend(q[:, :, :, :64])
     with pytest.raises(ValueError):
         kvq.QuantizedLayerKV(mode, "cuda", torch.float16).attend(q)
+
+
+def test_full_size_cross_variant_consistency(kvq):
+    """C5 per-GPU shard length (T = 65 536) on one KV head: no CPU oracle at this size, so the kernel variants check each other.
+    The register-tiled GQA kernel (fp32 FFMA2, 8 query heads on one KV head), the per-warp DP4A kernel (one query head per KV
+    head, codes repeated), the register-staged fp32 fallback (strided rows) and the paged instantiation all evaluate the same
+    softmax(q k^T) v: GQA == paged bit for bit, the others within fp32 accumulation noise."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, G, T, D = 1, 8, 65536, 128
+    kc = torch.randint(-127, 128, (B, 1, T, D), device="cuda", dtype=torch.int8, generator=g)
+    vc = torch.randint(0, 256, (B, 1, T, D // 2), device="cuda", dtype=torch.uint8, generator=g)
+    ks = torch.rand(T, device="cuda", generator=g) * 0.004 + 0.002
+    vs = torch.rand(T, device="cuda", generator=g) * 0.01 + 0.01
+    q = torch.randn(B, G, 1, D, device="cuda", generator=g)
+    gqa = kvq.decode_attention_quantized(q, kc, ks, 8, vc, vs, 4)
+    mha = kvq.decode_attention_quantized(q, kc.expand(B, G, T, D).contiguous(), ks, 8, vc.expand(B, G, T, D // 2).contiguous(), vs, 4)
+    torch.testing.assert_close(mha, gqa, rtol=2e-4, atol=2e-5)
+    # strided rows (a [B,H,T,2W] buffer viewed at half width) take the register-staged fp32 kernel
+    kpad = torch.zeros(B, 1, T, 2 * D, device="cuda", dtype=torch.int8)
+    kpad[..., :D] = kc
+    vpad = torch.zeros(B, 1, T, D, device="cuda", dtype=torch.uint8)
+    vpad[..., : D // 2] = vc
+    split = kvq.decode_attention_quantized(q, kpad[..., :D], ks, 8, vpad[..., : D // 2], vs, 4)
+    torch.testing.assert_close(split, gqa, rtol=2e-4, atol=2e-5)
+    # paged: same tokens in shuffled 128-token blocks
+    bs = 128
+    nb = T // bs
+    perm = torch.randperm(nb, device="cuda", generator=g)
+    table = torch.empty(nb, dtype=torch.int32, device="cuda")
+    table[:] = perm.to(torch.int32)
+    k_pool = torch.empty(nb, B, 1, bs, D, device="cuda", dtype=torch.int8)
+    v_pool = torch.empty(nb, B, 1, bs, D // 2, device="cuda", dtype=torch.uint8)
+    k_pool[perm] = kc.view(B, 1, nb, bs, D).permute(2, 0, 1, 3, 4)
+    v_pool[perm] = vc.view(B, 1, nb, bs, D // 2).permute(2, 0, 1, 3, 4)
+    ks_pool = torch.empty(nb, bs, device="cuda")
+    vs_pool = torch.empty(nb, bs, device="cuda")
+    ks_pool[perm] = ks.view(nb, bs)
+    vs_pool[perm] = vs.view(nb, bs)
+    paged = kvq.decode_attention_paged(q, k_pool, ks_pool, 8, v_pool, vs_pool, 4, table, T)
+    assert torch.equal(paged, gqa)
+    # weights sum to one: with V == const the output is that constant (exact up to the scale's rounding), for every variant
+    vc1 = torch.full_like(vc, 0xBB)  # nibble 11 -> code +3
+    one = kvq.decode_attention_quantized(q, kc, ks, 8, vc1, torch.full_like(vs, 0.5), 4)
+    torch.testing.assert_close(one, torch.full_like(one, 1.5), rtol=1e-5, atol=0)
