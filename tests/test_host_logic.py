@@ -96,3 +96,22 @@ def test_reference_import_root_alias():
     env = {**os.environ, "PYTHONPATH": root}
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-800:]
+
+
+def test_paged_quantized_store_host_checks():
+    """No GPU needed: constructor validation, and CPU tensors are refused (there is no CPU path)."""
+    import kvq_b200
+    for bad in (0, 8, 48, 100):
+        with pytest.raises(ValueError):
+            kvq_b200.PagedQuantizedLayerKV("int8", block_size=bad)
+    with pytest.raises(AssertionError):
+        kvq_b200.PagedQuantizedLayerKV("int3")
+    p = kvq_b200.PagedQuantizedLayerKV("mixed", block_size=32)
+    assert (p.k_bits, p.v_bits, len(p), p.num_blocks(), p.allocated_bytes()) == (8, 4, 0, 0, 0)
+    x = torch.zeros(1, 2, 3, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p.append_tokens(x, x)
+    with pytest.raises(ValueError):
+        p.attend(torch.zeros(1, 2, 1, 64))
+    with pytest.raises(ValueError):
+        p.get_kv()
