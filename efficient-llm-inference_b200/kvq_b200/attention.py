@@ -16,6 +16,28 @@ import torch
 from . import _lib as L
 
 
+def run_grouped(q: torch.Tensor, H: int, supported, call):
+    """The kernels are built for Hq/H in `supported` (powers of two <= 8).  Any other grouping -- Qwen2-7B's 7 query heads
+    per KV head, 3, 5, 6, or more than 8 -- runs as chunks of at most 8 query heads per KV head, each padded with zero
+    queries to the next supported size (a zero query gives a uniform softmax that is simply dropped).
+    `call(q_sub)` evaluates q_sub [B, H*g, 1, D] with g in `supported` and returns [B, H*g, 1, D]."""
+    B, Hq, _, D = q.shape
+    if Hq % H:
+        raise RuntimeError("Hq must be a multiple of H")
+    G = Hq // H
+    if G in supported:
+        return call(q)
+    q5 = q.contiguous().view(B, H, G, 1, D)
+    outs = []
+    for c0 in range(0, G, 8):
+        g = min(8, G - c0)
+        gp = min(x for x in supported if x >= g)
+        qs = q.new_zeros((B, H, gp, 1, D))
+        qs[:, :, :g] = q5[:, :, c0: c0 + g]
+        outs.append(call(qs.view(B, H * gp, 1, D)).view(B, H, gp, 1, D)[:, :, :g])
+    return torch.cat(outs, dim=2).reshape(B, Hq, 1, D)
+
+
 @torch.no_grad()
 def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales: torch.Tensor, k_bits: int,
                                v_codes: torch.Tensor, v_scales: torch.Tensor, v_bits: int,
@@ -25,7 +47,8 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
     """out[b,hq] = softmax_t(q[b,hq] . K[b,hq//G,t] * sm_scale) @ V[b,hq//G]  with K/V = codes * scale[t].
 
     q [B,Hq,1,D] (fp32/fp16/bf16); k_codes int8 [B,H,T,D] (k_bits 8) or uint8 [B,H,T,D/2] (k_bits 4);
-    k_scales fp32 [T]; v likewise.  G = Hq/H in {1,2,4,8}; D in {64,128}.  Returns [B,Hq,1,D].
+    k_scales fp32 [T]; v likewise.  D in {64,128}; kernels exist for Hq/H in {1,2,4,8}, any other grouping is run in padded
+    chunks (run_grouped).  Returns [B,Hq,1,D].
     k_cur / v_cur (optional, [B,H,1,D]): the decode step's own token, attended to exactly (unquantized) on top
     of the T cached tokens, as the reference's loop does.
     """
@@ -34,6 +57,10 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
         raise RuntimeError("q must be [B, Hq, 1, D] (one decode token)")
     B, Hq, _, D = q.shape
     H, T = k_codes.size(1), k_codes.size(2)
+    if H and Hq % H == 0 and Hq // H not in (1, 2, 4, 8):
+        return run_grouped(q, H, (1, 2, 4, 8), lambda qs: decode_attention_quantized(
+            qs, k_codes, k_scales, k_bits, v_codes, v_scales, v_bits, sm_scale=sm_scale if sm_scale is not None else float(D) ** -0.5,
+            out_dtype=out_dtype, workspace=workspace, k_cur=k_cur, v_cur=v_cur))
     if k_codes.size(0) != B or v_codes.size(0) != B or v_codes.size(1) != H or v_codes.size(2) != T:
         raise RuntimeError("K / V code tensors do not match q")
     if k_scales.dtype != torch.float32 or v_scales.dtype != torch.float32:
@@ -79,7 +106,7 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
 
     k_pool int8 [n_phys,B,H,block_size,D] (k_bits 8) or uint8 [..., D/2] (k_bits 4), contiguous; k_scale_pool fp32
     [n_phys, block_size]; v likewise; block_table int32 [>= ceil(seq_len / block_size)] (device): logical -> physical
-    block; seq_len = tokens stored.  G = Hq/H in {1,4,8}; block_size a power of two >= 16.
+    block; seq_len = tokens stored.  Kernels for Hq/H in {1,4,8}, other groupings in padded chunks; block_size a power of two >= 16.
     (The reference's PagedKVCache re-concatenates its blocks before every use: implementations.py:83-106.)"""
     L.require_cuda(q, k_pool, v_pool, k_scale_pool, v_scale_pool, block_table)
     if q.dim() != 4 or q.size(2) != 1:
@@ -90,6 +117,11 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
     H, bs = k_pool.size(2), k_pool.size(3)
     if k_pool.size(1) != B or v_pool.size(1) != B or v_pool.size(2) != H or v_pool.size(3) != bs:
         raise RuntimeError("K / V pools do not match q")
+    if H and Hq % H == 0 and Hq // H not in (1, 4, 8):  # the paged instantiations exist for 1, 4 and 8 query heads per KV head
+        return run_grouped(q, H, (1, 4, 8), lambda qs: decode_attention_paged(
+            qs, k_pool, k_scale_pool, k_bits, v_pool, v_scale_pool, v_bits, block_table, seq_len,
+            sm_scale=sm_scale if sm_scale is not None else float(D) ** -0.5, out_dtype=out_dtype, workspace=workspace,
+            k_cur=k_cur, v_cur=v_cur))
     if k_scale_pool.dtype != torch.float32 or v_scale_pool.dtype != torch.float32:
         raise RuntimeError("attention reads fp32 scales")
     if tuple(k_scale_pool.shape) != (k_pool.size(0), bs) or tuple(v_scale_pool.shape) != (v_pool.size(0), bs):

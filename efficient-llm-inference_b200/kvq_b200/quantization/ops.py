@@ -513,6 +513,10 @@ class QuantizedLayerKV:
             raise RuntimeError("q must be [B, Hq, 1, D] matching the cache")
         B, Hq, _, D = q.shape
         H = k.codes.size(1)
+        if Hq % H == 0 and Hq // H not in (1, 2, 4, 8):
+            from ..attention import run_grouped
+            return run_grouped(q, H, (1, 2, 4, 8), lambda qs: self.attend(qs, T, k_cur, v_cur, float(D) ** -0.5 if sm_scale is None else sm_scale,
+                                                                         out_dtype))
         if (k_cur is None) != (v_cur is None):
             raise RuntimeError("k_cur and v_cur must be given together")
         if k_cur is not None:

@@ -39,7 +39,8 @@ def test_golden_attention(kvq):
 @pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
 @pytest.mark.parametrize("B,Hq,H,T,D", [(2, 4, 4, 300, 64), (1, 8, 8, 1000, 128), (2, 8, 2, 513, 128), (1, 16, 2, 2000, 64),
                                          (16, 12, 12, 1024, 64), (1, 8, 1, 5000, 128), (2, 4, 2, 1, 128), (1, 2, 2, 129, 64),
-                                         (2, 8, 2, 700, 64), (3, 16, 4, 257, 128), (1, 32, 4, 40000, 128)])
+                                         (2, 8, 2, 700, 64), (3, 16, 4, 257, 128), (1, 32, 4, 40000, 128),
+                                         (1, 3, 3, 1, 64), (2, 2, 2, 17, 128), (1, 8, 1, 1, 128), (2, 8, 2, 2, 64), (1, 1, 1, 33000, 128)])
 def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
     g = torch.Generator().manual_seed(B * 1000 + T)
     k = torch.randn(B, H, T, D, generator=g)
@@ -84,8 +85,8 @@ def test_bad_arguments(kvq):
     with pytest.raises(RuntimeError, match="head_dim"):
         kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)
     q = torch.zeros(1, 3, 1, 64, device="cuda")
-    kc = torch.zeros(1, 1, 4, 64, dtype=torch.int8, device="cuda")
-    with pytest.raises(RuntimeError, match="Hq/H"):
+    kc = torch.zeros(1, 2, 4, 64, dtype=torch.int8, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of H"):  # (3 query heads on ONE KV head would run, zero-padded to 4)
         kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)
 
 
@@ -207,3 +208,27 @@ def test_full_size_cross_variant_consistency(kvq):
     vc1 = torch.full_like(vc, 0xBB)  # nibble 11 -> code +3
     one = kvq.decode_attention_quantized(q, kc, ks, 8, vc1, torch.full_like(vs, 0.5), 4)
     torch.testing.assert_close(one, torch.full_like(one, 1.5), rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("G", [3, 5, 6, 7, 12, 16])
+def test_any_group_size(kvq, oracle, G):
+    """Groupings the kernels are not built for (Qwen2-7B: 7 query heads per KV head) run as zero-padded chunks of <= 8."""
+    g = torch.Generator().manual_seed(G)
+    B, H, T, D = 2, 2, 333, 64
+    k, v = torch.randn(B, H, T, D, generator=g), torch.randn(B, H, T, D, generator=g)
+    q = torch.randn(B, H * G, 1, D, generator=g)
+    kcur, vcur = torch.randn(B, H, 1, D, generator=g), torch.randn(B, H, 1, D, generator=g)
+    layer = kvq.QuantizedLayerKV("mixed", "cuda", torch.float32)
+    layer.append_tokens(k.cuda(), v.cuda())
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    want = oracle.decode_attention(q, kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
+    got = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+    assert torch.equal(layer.attend(q.cuda()), got)
+    paged = kvq.PagedQuantizedLayerKV("mixed", block_size=32, compute_dtype=torch.float32)
+    paged.append_tokens(k.cuda(), v.cuda())
+    torch.testing.assert_close(paged.attend(q.cuda()).cpu(), want, rtol=1e-4, atol=1e-5)
+    # with the step's own token: equals attention over T + 1 tokens whose last one is exact -> compare the two wrappers
+    a = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb, k_cur=kcur.cuda(), v_cur=vcur.cuda())
+    b = layer.attend(q.cuda(), None, kcur.cuda(), vcur.cuda())
+    assert torch.equal(a, b)

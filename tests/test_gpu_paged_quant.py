@@ -100,7 +100,10 @@ def test_bad_arguments(kvq):
         p.attend(torch.zeros(1, 2, 1, 64, device="cuda"))
     k, v = _kv(1, 2, 40, 64, 1, torch.float16)
     p.append_tokens(k, v)
-    with pytest.raises(RuntimeError):  # Hq / H = 2 is not built for the paged path
-        p.attend(torch.zeros(1, 4, 1, 64, device="cuda", dtype=torch.float16))
+    # Hq / H = 2 has no paged instantiation: it runs zero-padded as 4 query heads per KV head
+    q2 = torch.randn(1, 4, 1, 64, device="cuda", dtype=torch.float16)
+    flat = kvq.QuantizedLayerKV("int8", "cuda", torch.float16)
+    flat.append_tokens(k, v)
+    torch.testing.assert_close(p.attend(q2), flat.attend(q2), rtol=2e-3, atol=2e-3)
     with pytest.raises(RuntimeError):
         p.append_tokens(k[:, :1], v[:, :1])
