@@ -600,18 +600,22 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_token_kernel(const char
     constexpr int kIn = CodeIn<ODT, BITS>::kBytes;
     int ti; int64_t c0, c1;
     flat_split(w, ti, c0, c1);
+    const uint32_t vpp32 = (uint32_t)vpp;  // the host takes this path only for planes of fewer than 2^31 vectors
     for (int64_t c = c0; c < c1; c += w.cstep) {
         const int64_t base = c * (kThreads * UNROLL);
-        const int64_t plane0 = base / vpp, within0 = base - plane0 * vpp;  // uniform over the CTA
+        const int64_t plane0 = base / vpp;  // uniform over the CTA: one 64-bit division per chunk, 32-bit steps per vector
+        const uint32_t within0 = (uint32_t)(base - plane0 * vpp);
+        const char* cbase = codes + plane0 * plane_stride;
         Raw<kIn> r[UNROLL];
         ScaleArg<PK> sv[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t j = base + u * kThreads + threadIdx.x;
             if (j < n_vec) {
-                int64_t plane = plane0, pos = within0 + u * kThreads + threadIdx.x;
-                while (pos >= vpp) { pos -= vpp; ++plane; }  // a chunk reaches into the next plane(s) only at a plane's end
-                r[u].load(codes + plane * plane_stride + pos * kIn);
+                uint32_t pos = within0 + u * kThreads + threadIdx.x;
+                const char* cp = cbase;
+                while (pos >= vpp32) { pos -= vpp32; cp += plane_stride; }  // a chunk reaches into the next plane(s) only at a plane's end
+                r[u].load(cp + (size_t)pos * kIn);
                 sv[u].load(scale, scale_dtype, pos >> vpr_shift);
             }
         }
@@ -873,7 +877,8 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
             KVQ_DISPATCH_DT(out_dtype, dequant_flat_kernel<DT, BITS, false, U><<<grid, kThreads, 0, st>>>(
                                            (const char*)codes, n_vec, scale, scale_dtype, (uint4*)out, w));
         }
-    } else if (per_token && rows_ok && cs.sT == W && cs.sB == H * cs.sH && ((D * oes / 16) & (D * oes / 16 - 1)) == 0) {
+    } else if (per_token && rows_ok && cs.sT == W && cs.sB == H * cs.sH && ((D * oes / 16) & (D * oes / 16 - 1)) == 0 &&
+               T * (D * oes / 16) < (1LL << 30)) {
         // planes of T contiguous rows at a uniform stride (the cache store: capacity >= T): flat stream over the output
         const int64_t n_vec = n * oes / 16;
         constexpr int U = 4;
