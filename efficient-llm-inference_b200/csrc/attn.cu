@@ -947,7 +947,7 @@ template <int KBITS, int VBITS, int G, int D> struct GqaCfg {
     static constexpr int LPR = D / 16;                          // K: lanes per token row, 16 channels each
     // q in shared memory: [variant 2][chunk LPR][channel 16][G heads], padded so that the LPR lanes of a row, which read
     // different chunks / variants / head groups in one LDS.128, hit 32 distinct banks (pads found by exhaustive search)
-    static constexpr int CP = 16 * G + (G == 8 && LPR == 8 ? 8 : 4);
+    static constexpr int CP = 16 * G + (G == 8 && LPR == 8 ? 8 : 4);  // G = 2: 36, chunk kc starts at bank 4 kc (LDS.128 of two channels)
     static constexpr int VS = LPR * CP + (G == 8 && LPR == 4 ? 4 : 0);
     static constexpr int LPRV = D / 4, VRW = 32 / LPRV;         // V: lanes per token row (4 channels each), rows per warp pass
     static constexpr int kRed = kWarps * VRW * G * D * 4;       // final merge of the warps' partials aliases the ring
@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
     constexpr int S = C::kStages, PD = S > 2 ? S - 2 : 1;       // tiles in flight ahead of the math
     constexpr int GP = G / 2;                                   // head pairs
     constexpr int kVUnroll = KVQ_ATTN_GQA_VUNROLL;
-    static_assert(G == 4 || G == 8, "G");
+    static_assert(G == 2 || G == 4 || G == 8, "G");
     static_assert(RT >= 1 && RT * KSUB * RPP == WR, "tiling");
 
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1107,16 +1107,28 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
                 float f[RT][4];
 #pragma unroll
                 for (int r = 0; r < RT; ++r) cvt4<KBITS>(kw[r], e4, f[r]);
+                if constexpr (G == 2) {  // one head pair: an LDS.128 of q covers two channels
 #pragma unroll
-                for (int ee = 0; ee < 4; ++ee) {
-#pragma unroll
-                    for (int m = 0; m < G / 4; ++m) {
-                        const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + ee) * G + 4 * (m ^ mm));
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + 2 * e2) * G);
 #pragma unroll
                         for (int r = 0; r < RT; ++r) {
-                            const f32x2 fb = pack2(f[r][ee], f[r][ee]);
-                            a[r][2 * m] = ffma2(qq.x, fb, a[r][2 * m]);
-                            a[r][2 * m + 1] = ffma2(qq.y, fb, a[r][2 * m + 1]);
+                            a[r][0] = ffma2(qq.x, pack2(f[r][2 * e2], f[r][2 * e2]), a[r][0]);
+                            a[r][0] = ffma2(qq.y, pack2(f[r][2 * e2 + 1], f[r][2 * e2 + 1]), a[r][0]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ee = 0; ee < 4; ++ee) {
+#pragma unroll
+                        for (int m = 0; m < G / 4; ++m) {
+                            const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(q_lane + (4 * e4 + ee) * G + 4 * (m ^ mm));
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) {
+                                const f32x2 fb = pack2(f[r][ee], f[r][ee]);
+                                a[r][2 * m] = ffma2(qq.x, fb, a[r][2 * m]);
+                                a[r][2 * m + 1] = ffma2(qq.y, fb, a[r][2 * m + 1]);
+                            }
                         }
                     }
                 }
@@ -1194,6 +1206,11 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
 
         // ---- V phase: [G heads x 4 channels] accumulators, two heads per FFMA2
         if (moved) {  // warp-uniform: the maxima settle after the first tiles
+            if constexpr (G == 2) {
+                const f32x2 al = *reinterpret_cast<const f32x2*>(alpha_w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[0][e] = fmul2(acc[0][e], al);
+            }
 #pragma unroll
             for (int g4 = 0; g4 < G / 4; ++g4) {
                 const ulonglong2 al = *reinterpret_cast<const ulonglong2*>(alpha_w + 4 * g4);
@@ -1209,6 +1226,11 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
             else vw[0] = *reinterpret_cast<const unsigned short*>(vsb + ps * VRW * C::kVRow);
             float f[4];
             cvt4<VBITS>(vw, 0, f);
+            if constexpr (G == 2) {
+                const f32x2 pp = *reinterpret_cast<const f32x2*>(p_w + (ps * VRW + vrow) * G);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[0][e] = ffma2(pp, pack2(f[e], f[e]), acc[0][e]);
+            }
             const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(p_w + (ps * VRW + vrow) * G);
 #pragma unroll
             for (int g4 = 0; g4 < G / 4; ++g4) {
@@ -1710,6 +1732,10 @@ int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tm
         if (tma && !fp32_only && block_wide && !paged) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
         if (tma && (!fp32_only || paged)) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
     }
+    if constexpr (G == 2) {  // KVQ_ATTN_G2_BLOCK=1: the block-wide fp32 TMA kernel of the first versions, for A/B runs
+        static const bool g2_block = getenv("KVQ_ATTN_G2_BLOCK") != nullptr;
+        if (tma && (!g2_block || P.table != nullptr)) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
+    }
     if constexpr (G <= 2) {
         if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
     } else {  // GQA groups of 4 / 8 are FFMA-bound: register-tiled variant (KVQ_ATTN_GQA_OLD=1 keeps the first version for A/B runs)
@@ -1733,7 +1759,7 @@ int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool
 
 int choose_splits(int64_t B, int64_t H, int64_t T, int64_t G) {
     // one wave of 256-thread CTAs at the variant's CTAs per SM
-    const int64_t per_sm = G == 1 ? KVQ_ATTN_MHA_CTAS_PER_SM : G == 2 ? KVQ_ATTN_CTAS_PER_SM : KVQ_ATTN_GQA_CTAS_PER_SM;
+    const int64_t per_sm = G == 1 ? KVQ_ATTN_MHA_CTAS_PER_SM : KVQ_ATTN_GQA_CTAS_PER_SM;
     const int64_t target = per_sm * sm_count();
     int64_t n = (target + B * H - 1) / (B * H);
     const int64_t max_n = (T + 255) / 256;
@@ -1843,7 +1869,7 @@ extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_p
     KVQ_REQUIRE(B >= 1 && H >= 1 && Hq >= 1 && T >= 1 && T <= 0x7fffffff && B <= 65535 && H <= 65535, "bad shape");
     KVQ_REQUIRE(Hq % H == 0, "Hq must be a multiple of H");
     const int64_t G = Hq / H;
-    KVQ_REQUIRE(G == 1 || G == 4 || G == 8, "decode_attn_paged: Hq/H must be 1, 4 or 8 (got %lld)", (long long)G);
+    KVQ_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "decode_attn_paged: Hq/H must be 1, 2, 4 or 8 (got %lld)", (long long)G);
     KVQ_REQUIRE(block_size >= 16 && (block_size & (block_size - 1)) == 0, "decode_attn_paged: block_size must be a power of two >= 16 (got %lld)",
                 (long long)block_size);
     KVQ_REQUIRE(n_splits >= 1, "n_splits must be >= 1");

@@ -106,7 +106,7 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
 
     k_pool int8 [n_phys,B,H,block_size,D] (k_bits 8) or uint8 [..., D/2] (k_bits 4), contiguous; k_scale_pool fp32
     [n_phys, block_size]; v likewise; block_table int32 [>= ceil(seq_len / block_size)] (device): logical -> physical
-    block; seq_len = tokens stored.  Kernels for Hq/H in {1,4,8}, other groupings in padded chunks; block_size a power of two >= 16.
+    block; seq_len = tokens stored.  Kernels for Hq/H in {1,2,4,8}, other groupings in padded chunks; block_size a power of two >= 16.
     (The reference's PagedKVCache re-concatenates its blocks before every use: implementations.py:83-106.)"""
     L.require_cuda(q, k_pool, v_pool, k_scale_pool, v_scale_pool, block_table)
     if q.dim() != 4 or q.size(2) != 1:
@@ -117,8 +117,8 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
     H, bs = k_pool.size(2), k_pool.size(3)
     if k_pool.size(1) != B or v_pool.size(1) != B or v_pool.size(2) != H or v_pool.size(3) != bs:
         raise RuntimeError("K / V pools do not match q")
-    if H and Hq % H == 0 and Hq // H not in (1, 4, 8):  # the paged instantiations exist for 1, 4 and 8 query heads per KV head
-        return run_grouped(q, H, (1, 4, 8), lambda qs: decode_attention_paged(
+    if H and Hq % H == 0 and Hq // H not in (1, 2, 4, 8):
+        return run_grouped(q, H, (1, 2, 4, 8), lambda qs: decode_attention_paged(
             qs, k_pool, k_scale_pool, k_bits, v_pool, v_scale_pool, v_bits, block_table, seq_len,
             sm_scale=sm_scale if sm_scale is not None else float(D) ** -0.5, out_dtype=out_dtype, workspace=workspace,
             k_cur=k_cur, v_cur=v_cur))

@@ -261,7 +261,7 @@ KVQ_API int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, 
  *   k/v_scale_pool      : float [n_phys][block_size], one scale per token
  *   block_table         : device int32 [ceil(T / block_size)]: logical block -> physical block
  *   block_size          : power of two >= 16
- * Hq / H in {1, 4, 8}.  Workspace / n_splits as for kvq_decode_attn.  Results are bit-identical to kvq_decode_attn_ex on the
+ * Hq / H in {1, 2, 4, 8}.  Workspace / n_splits as for kvq_decode_attn.  Results are bit-identical to kvq_decode_attn_ex on the
  * same tokens stored contiguously. */
 KVQ_API int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
                           const float* k_scale_pool, const void* v_pool, int v_bits, const int64_t v_pool_stride3[3],

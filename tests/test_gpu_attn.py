@@ -40,7 +40,8 @@ def test_golden_attention(kvq):
 @pytest.mark.parametrize("B,Hq,H,T,D", [(2, 4, 4, 300, 64), (1, 8, 8, 1000, 128), (2, 8, 2, 513, 128), (1, 16, 2, 2000, 64),
                                          (16, 12, 12, 1024, 64), (1, 8, 1, 5000, 128), (2, 4, 2, 1, 128), (1, 2, 2, 129, 64),
                                          (2, 8, 2, 700, 64), (3, 16, 4, 257, 128), (1, 32, 4, 40000, 128),
-                                         (1, 3, 3, 1, 64), (2, 2, 2, 17, 128), (1, 8, 1, 1, 128), (2, 8, 2, 2, 64), (1, 1, 1, 33000, 128)])
+                                         (1, 3, 3, 1, 64), (2, 2, 2, 17, 128), (1, 8, 1, 1, 128), (2, 8, 2, 2, 64), (1, 1, 1, 33000, 128),
+                                         (2, 8, 4, 777, 128), (1, 24, 12, 1500, 64), (4, 4, 2, 130, 64), (1, 2, 1, 9000, 128)])
 def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
     g = torch.Generator().manual_seed(B * 1000 + T)
     k = torch.randn(B, H, T, D, generator=g)
