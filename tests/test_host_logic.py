@@ -115,3 +115,27 @@ def test_paged_quantized_store_host_checks():
         p.attend(torch.zeros(1, 2, 1, 64))
     with pytest.raises(ValueError):
         p.get_kv()
+
+
+def test_run_grouped_chunks_and_pads():
+    """Query-head groupings the kernels are not built for: chunks of <= 8 heads per KV head, zero-padded to a supported size,
+    results put back in order (pure host logic: checked with a stand-in for the kernel call)."""
+    from kvq_b200.attention import run_grouped
+    B, H, D = 2, 3, 8
+    for G in (1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 17):
+        q = torch.randn(B, H * G, 1, D)
+        seen = []
+
+        def call(qs):
+            g = qs.size(1) // H
+            seen.append(g)
+            assert g in (1, 2, 4, 8)
+            return qs * 2 + torch.arange(H).view(1, H, 1, 1, 1).expand(B, H, g, 1, 1).reshape(B, H * g, 1, 1)  # depends on the KV head
+
+        out = run_grouped(q, H, (1, 2, 4, 8), call)
+        want = q * 2 + torch.arange(H).repeat_interleave(G).view(1, H * G, 1, 1)
+        assert torch.equal(out, want)
+        expect = [G] if G in (1, 2, 4, 8) else [min(x for x in (1, 2, 4, 8) if x >= min(8, G - c)) for c in range(0, G, 8)]
+        assert seen == expect
+    with pytest.raises(RuntimeError):
+        run_grouped(torch.zeros(1, 5, 1, 8), 2, (1, 2, 4, 8), lambda x: x)
