@@ -34,6 +34,9 @@ class _PagedStream:
         self.free: List[int] = []
         self.T = 0                                  # tokens stored (logical 0 .. T-1); block 0 is always full-from-0
         self.D = 0
+        self._stride3 = None
+        self._stride3_of = None
+        self._bits_scratch: Optional[torch.Tensor] = None
 
     def _grow(self, x: torch.Tensor, n_blocks: int) -> None:
         B, H, _, D = x.shape
@@ -74,20 +77,26 @@ class _PagedStream:
                 self.table_host.append(self.free.pop())
             self._sync_table()
         lib, dt, stream = L.lib(), L.dtype_code(x.dtype), L.stream_ptr(x.device)
+        codes = self.codes
+        if self._stride3_of is not codes:  # {sB,sH,sT} of one block, bytes == elements for the 1-byte codes
+            self._stride3, self._stride3_of = L.I64x3(codes.stride(1), codes.stride(2), codes.stride(3)), codes
+        bits = self._bits_scratch
+        if bits is None or bits.numel() < min(n, self.bs) or bits.device != x.device:
+            bits = self._bits_scratch = torch.empty(max(self.bs, 64), dtype=torch.int32, device=x.device)
+        es = self.scales.element_size()
         done = 0
-        while done < n:
+        while done < n:  # destination pointers by arithmetic on the pools: the decode loop comes through here every step
             t = self.T + done
             blk, w = divmod(t, self.bs)
             m = min(self.bs - w, n - done)
             phys = self.table_host[blk]
-            src = x[:, :, done: done + m]
-            dst = self.codes[phys][:, :, w: w + m]
-            sc, s32 = self.scales[phys, w: w + m], self.scales_f32[phys, w: w + m]
-            bits = torch.empty(m, dtype=torch.int32, device=x.device)
+            src = x if m == n else x[:, :, done: done + m]
             sh, st = L.shape_stride(src)
-            L.check(lib.kvq_quant_per_token_fused(src.data_ptr(), dt, sh, st, self.bits, float(eps), dst.data_ptr(),
-                                                  L.stride3(dst), sc.data_ptr(), s32.data_ptr(), bits.data_ptr(), stream),
-                    "kvq_quant_per_token_fused")
+            slot = phys * self.bs + w
+            L.check(lib.kvq_quant_per_token_fused(src.data_ptr(), dt, sh, st, self.bits, float(eps),
+                                                  codes.data_ptr() + phys * codes.stride(0) + w * codes.stride(3), self._stride3,
+                                                  self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
+                                                  bits.data_ptr(), stream), "kvq_quant_per_token_fused")
             L.count_launch()
             done += m
         self.T += n
@@ -199,11 +208,42 @@ class PagedQuantizedLayerKV:
         n = len(self) if seq_len is None else int(seq_len)
         if not 1 <= n <= len(self):
             raise ValueError(f"seq_len must be in [1, {len(self)}]")
-        if self._ws is None:
-            self._ws = torch.empty(8 << 20, dtype=torch.float32, device=q.device)
-        return decode_attention_paged(q, self._k.codes, self._k.scales_f32, self.k_bits, self._v.codes, self._v.scales_f32,
-                                      self.v_bits, self._k.table, n, sm_scale=sm_scale, out_dtype=out_dtype,
-                                      workspace=self._ws, k_cur=k_cur, v_cur=v_cur)
+        k, v = self._k, self._v
+        B, H, bs = k.codes.size(1), k.codes.size(2), self.block_size
+        if q.dim() != 4 or q.size(2) != 1 or q.size(0) != B or q.size(3) != k.D or not q.is_cuda:
+            raise RuntimeError("q must be a CUDA tensor [B, Hq, 1, D] matching the cache")
+        Hq, D = q.size(1), q.size(3)
+        if Hq % H or Hq // H not in (1, 2, 4, 8) or (k_cur is None) != (v_cur is None):
+            if self._ws is None:
+                self._ws = torch.empty(8 << 20, dtype=torch.float32, device=q.device)
+            return decode_attention_paged(q, k.codes, k.scales_f32, self.k_bits, v.codes, v.scales_f32, self.v_bits, k.table, n,
+                                          sm_scale=sm_scale, out_dtype=out_dtype, workspace=self._ws, k_cur=k_cur, v_cur=v_cur)
+        # per-step path of KvqFusedCache: the same C call without the wrapper's tensor bookkeeping
+        import ctypes
+        if k_cur is not None:
+            if tuple(k_cur.shape) != (B, H, 1, D) or tuple(v_cur.shape) != (B, H, 1, D):
+                raise RuntimeError("k_cur / v_cur must be [B, H, 1, D]")
+            k_cur, v_cur = k_cur.to(q.dtype).contiguous(), v_cur.to(q.dtype).contiguous()
+        qc = q.contiguous()
+        out_dtype = out_dtype or q.dtype
+        out = torch.empty((B, Hq, 1, D), dtype=out_dtype, device=q.device)
+        with L.device_guard(q):
+            lib = L.lib()
+            ns = ctypes.c_int(1)
+            nbytes = lib.kvq_decode_attn_workspace_bytes(B, Hq, H, n, D, ctypes.byref(ns))
+            ws = self._ws
+            if ws is None or ws.numel() * 4 < nbytes or ws.device != q.device:
+                ws = self._ws = torch.empty(max(nbytes, 1 << 20) // 4, dtype=torch.float32, device=q.device)
+            L.check(lib.kvq_decode_attn_paged(qc.data_ptr(), L.dtype_code(q.dtype), k.codes.data_ptr(), self.k_bits, None,
+                                              k.scales_f32.data_ptr(), v.codes.data_ptr(), self.v_bits, None, v.scales_f32.data_ptr(),
+                                              k.table.data_ptr(), bs, B, Hq, H, n, D,
+                                              float(D) ** -0.5 if sm_scale is None else float(sm_scale),
+                                              k_cur.data_ptr() if k_cur is not None else None,
+                                              v_cur.data_ptr() if v_cur is not None else None, out.data_ptr(),
+                                              L.dtype_code(out_dtype), ws.data_ptr(), ns.value, L.stream_ptr(q.device)),
+                    "kvq_decode_attn_paged")
+            L.count_launch(2)
+        return out
 
     def allocated_bytes(self) -> int:
         """Bytes of the blocks in use (codes + fp16-sized scales as the reference counts them, ops.py:357-363)."""
