@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--window", type=int, default=256)
     ap.add_argument("--evict-window", type=int, default=0, help="with --fused: compose the quantized store with a sliding window")
+    ap.add_argument("--paged-block", type=int, default=0, help="with --fused: keep the codes in a paged pool of this block size")
     ap.add_argument("--fused", action="store_true", help="quant_* methods through KvqFusedCache + fused decode attention")
     ap.add_argument("--methods", nargs="*", default=["full_cache", "quant_int8", "quant_int4", "quant_mixed", "sliding_window",
                                                      "strided_cache", "block_cache", "budget_cache", "chunked_cache", "paged_attention"])
@@ -67,12 +68,15 @@ def main():
         kw = {"fused_attention": True} if (args.fused and args.impl == "kvq") else {}
         if kw and args.evict_window and method.startswith("quant_"):
             kw["evict"] = {"strategy": "sliding_window", "window_size": args.evict_window}
+        if kw and args.paged_block and method.startswith("quant_"):
+            kw["paged_block_size"] = args.paged_block
         if args.device == "cuda":
             bench.benchmark_method(["x"], method=method, max_new_tokens=4, window_size=args.window, **kw)  # warm
         t0 = time.time()
         r = bench.benchmark_method(["x"], method=method, max_new_tokens=args.new, window_size=args.window, **kw)
         r["fused_attention"] = bool(kw)
         r["evict"] = kw.get("evict")
+        r["paged_block_size"] = kw.get("paged_block_size")
         r["wall_sec"] = time.time() - t0
         r["batch"], r["prompt_len"], r["impl"], r["device"] = args.batch, args.prompt_len, args.impl, args.device
         r["tokens_per_sec_x_batch"] = r["tokens_per_sec"] * args.batch
