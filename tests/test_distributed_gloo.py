@@ -71,3 +71,43 @@ def test_allreduce_is_noop_without_group():
     from kvq_b200.distributed import allreduce_absmax_
     b = torch.tensor([5], dtype=torch.int32)
     assert allreduce_absmax_(b, None) is b
+
+
+def _worker_halves(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # bench.py's N > 1 step: the absmax words of the batch are reduced in two halves with async allreduce(MAX) on views of one
+        # buffer, each waited for just before its quantize launch -- must equal one allreduce over the whole buffer
+        n, half = 64, 32
+        g = torch.Generator().manual_seed(100 + rank)
+        bits = torch.rand(n, generator=g).view(torch.int32).clone()      # non-negative fp32 bit patterns: int order == float order
+        whole = bits.clone()
+        works = [dist.all_reduce(bits[lo: lo + cnt], op=dist.ReduceOp.MAX, async_op=True) for lo, cnt in ((0, half), (half, n - half))]
+        for w in works:
+            w.wait()
+        dist.all_reduce(whole, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(whole) for _ in range(world)]
+        dist.all_gather(gathered, whole)
+        ok = torch.equal(bits, whole) and all(torch.equal(t, whole) for t in gathered)
+        ok = ok and torch.equal(whole.view(torch.float32), torch.stack([torch.rand(n, generator=torch.Generator().manual_seed(100 + r))
+                                                                        for r in range(world)]).max(0).values)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_half_async_allreduce_equals_one_allreduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_halves, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
