@@ -18,6 +18,10 @@ namespace kvq {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef KVQ_GATHER_CTAS_PER_SM
+#define KVQ_GATHER_CTAS_PER_SM 128
+#endif
+constexpr int kGatherCtasPerSm = KVQ_GATHER_CTAS_PER_SM;  // compile-time tuning knob (r1c sweep)
 
 // device copy of the plan, 32-bit where the kernel needs speed (T <= INT32_MAX is enforced)
 struct PlanDev {
@@ -108,10 +112,15 @@ struct CopyGeom {
 // dst[p, j, :] = src[p, src_token(j), :].  A CTA owns a tile of destination rows: their source tokens are
 // evaluated once (one thread per row) into shared memory and reused for every plane (b, h) the CTA walks,
 // so the copy loop is LDS + two address IMADs + LDG.128 + STG.128 per 16 bytes, UNROLL loads in flight.
+// Batched form (srcs != nullptr): blockIdx.z is the tensor (all layers x {K, V} of a step share shape, strides and plan), so
+// the 256-320-row outputs of budget / prefix+window -- latency-bound as 64 separate 6 us launches -- become one launch.
 template <int UNROLL>
 __global__ void __launch_bounds__(kThreads) evict_gather_kernel(const char* __restrict__ src, char* __restrict__ dst,
-                                                               CopyGeom g, PlanDev pl, const int32_t* __restrict__ table) {
+                                                               CopyGeom g, PlanDev pl, const int32_t* __restrict__ table,
+                                                               const void* const* __restrict__ srcs = nullptr,
+                                                               void* const* __restrict__ dsts = nullptr) {
     __shared__ int src_row[kThreads * UNROLL];
+    if (srcs) { src = reinterpret_cast<const char*>(srcs[blockIdx.z]); dst = reinterpret_cast<char*>(dsts[blockIdx.z]); }
     int c, r0, rpp;
     if (g.shift >= 0) { c = threadIdx.x & (g.cpr - 1); r0 = threadIdx.x >> g.shift; rpp = kThreads >> g.shift; }
     else { c = threadIdx.x % g.cpr; r0 = threadIdx.x / g.cpr; rpp = kThreads / g.cpr; }
@@ -320,23 +329,23 @@ extern "C" int kvq_evict_indices_device(const kvq_evict_plan* plan, const int32_
     return check_launch("evict_indices");
 }
 
-extern "C" int kvq_evict_gather(const void* src, int elem_bytes, const int64_t shape[4], const int64_t stride[4],
-                                const kvq_evict_plan* plan, const int32_t* old_table, void* dst, const int64_t dst_stride3[3],
-                                kvq_stream_t stream) {
-    KVQ_REQUIRE(src && dst && shape && stride && plan, "null pointer");
+namespace kvq { namespace {
+// common body of kvq_evict_gather (n_tensors == 1, src / dst) and kvq_evict_gather_batched (device pointer tables)
+int run_gather(const void* src, void* dst, const void* const* srcs, void* const* dsts, int64_t n_tensors, bool ptrs_aligned,
+               int elem_bytes, const int64_t shape[4], const int64_t stride[4], const kvq_evict_plan* plan,
+               const int32_t* old_table, const int64_t dst_stride3[3], cudaStream_t st) {
     KVQ_REQUIRE(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4, "elem_bytes must be 1, 2 or 4");
     const int64_t B = shape[0], H = shape[1], T = shape[2], D = shape[3];
     KVQ_REQUIRE(B >= 0 && H >= 0 && D >= 0, "negative shape");
     KVQ_REQUIRE(T == plan->T, "plan was made for T=%lld, tensor has T=%lld", (long long)plan->T, (long long)T);
     KVQ_REQUIRE(!plan->needs_table || old_table, "plan needs old_table (float32 linspace produced duplicates)");
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_out = plan->n_total;
-    if (B * H * n_out * D == 0) return KVQ_OK;
+    if (B * H * n_out * D == 0 || n_tensors == 0) return KVQ_OK;
     const Stride3 ds = make_stride3(dst_stride3, H, n_out, D);
     const PlanDev pd = to_dev(*plan, old_table != nullptr);
     const int64_t rb = D * elem_bytes;
     auto a16 = [&](int64_t s) { return (s * elem_bytes) % 16 == 0; };
-    const bool fast = stride[3] == 1 && rb % 16 == 0 && rb / 16 <= kThreads && aligned16(src) && aligned16(dst) && a16(stride[0]) &&
+    const bool fast = stride[3] == 1 && rb % 16 == 0 && rb / 16 <= kThreads && ptrs_aligned && a16(stride[0]) &&
                       a16(stride[1]) && a16(stride[2]) && a16(ds.sB) && a16(ds.sH) && a16(ds.sT) && B * H <= 0x7fffffff;
     if (fast) {
         CopyGeom g{(int)(B * H), (int)H, stride[0] * elem_bytes, stride[1] * elem_bytes, stride[2] * elem_bytes,
@@ -348,13 +357,17 @@ extern "C" int kvq_evict_gather(const void* src, int elem_bytes, const int64_t s
         constexpr int U = 4;
         const int rpp = kThreads / g.cpr;
         const int64_t tiles = (n_out + (int64_t)rpp * U - 1) / ((int64_t)rpp * U);
-        static const int ctas_per_sm = [] { const char* e = getenv("KVQ_GATHER_CTAS_PER_SM"); const int n = e ? atoi(e) : 0; return n > 0 ? n : 128; }();
-        const int64_t total = (int64_t)sm_count() * ctas_per_sm;  // 128 short CTAs per SM: 6.25 TB/s vs 5.96 at 16 (r1c sweep)
+        // 128 short CTAs per SM: 6.25 TB/s vs 5.96 at 16 (profiles/r1c_grid_sweep.log); batched: that many over ALL tensors
+        int64_t total = ((int64_t)sm_count() * kGatherCtasPerSm + n_tensors - 1) / n_tensors;
+        if (total < 1) total = 1;
         int64_t gx = tiles < total ? tiles : total, gy = (total + gx - 1) / gx;
         if (gy > g.nP) gy = g.nP;
-        dim3 grid((unsigned)gx, (unsigned)(gy > 0 ? gy : 1));
-        evict_gather_kernel<U><<<grid, kThreads, 0, st>>>((const char*)src, (char*)dst, g, pd, old_table);
+        if (gy > 65535) gy = 65535;
+        dim3 grid((unsigned)gx, (unsigned)(gy > 0 ? gy : 1), (unsigned)n_tensors);
+        evict_gather_kernel<U><<<grid, kThreads, 0, st>>>((const char*)src, (char*)dst, g, pd, old_table, srcs, dsts);
     } else {
+        if (srcs) return fail(KVQ_ERR_UNSUPPORTED, "evict_gather_batched: rows must be 16-byte multiples with 16-byte-aligned strides and pointers "
+                                                   "(use kvq_evict_gather per tensor for other layouts)");
         const unsigned grid = gen_grid(B * H * n_out * D);
 #define KVQ_GG(E) evict_gather_generic_kernel<E><<<grid, kThreads, 0, st>>>((const E*)src, (E*)dst, B, H, D, stride[0], stride[1], \
                                                                            stride[2], stride[3], ds.sB, ds.sH, ds.sT, pd, old_table)
@@ -362,6 +375,71 @@ extern "C" int kvq_evict_gather(const void* src, int elem_bytes, const int64_t s
 #undef KVQ_GG
     }
     return check_launch("evict_gather");
+}
+} }
+
+extern "C" int kvq_evict_gather(const void* src, int elem_bytes, const int64_t shape[4], const int64_t stride[4],
+                                const kvq_evict_plan* plan, const int32_t* old_table, void* dst, const int64_t dst_stride3[3],
+                                kvq_stream_t stream) {
+    KVQ_REQUIRE(src && dst && shape && stride && plan, "null pointer");
+    return run_gather(src, dst, nullptr, nullptr, 1, aligned16(src) && aligned16(dst), elem_bytes, shape, stride, plan, old_table,
+                      dst_stride3, (cudaStream_t)stream);
+}
+
+extern "C" int kvq_evict_gather_batched(const void* const* srcs, void* const* dsts, int64_t n_tensors, int elem_bytes,
+                                        const int64_t shape[4], const int64_t stride[4], const kvq_evict_plan* plan,
+                                        const int32_t* old_table, const int64_t dst_stride3[3], kvq_stream_t stream) {
+    KVQ_REQUIRE(srcs && dsts && shape && stride && plan, "null pointer");
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535, "n_tensors out of range");
+    return run_gather(nullptr, nullptr, srcs, dsts, n_tensors, true, elem_bytes, shape, stride, plan, old_table, dst_stride3,
+                      (cudaStream_t)stream);
+}
+
+// The older region's tokens of a budget plan whose float32 linspace produced duplicates (plan->needs_table), built ON THE
+// DEVICE: idx[i] = trunc(linspace(i)), keep i when idx[i] != idx[i-1] (torch.unique_consecutive, implementations.py:279-282),
+// compacted by a block-wide scan.  table: int32 [plan->n_old].
+namespace kvq { namespace {
+__global__ void __launch_bounds__(1024) budget_table_kernel(PlanDev pl, int32_t* __restrict__ table) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < pl.budget; base += 1024) {
+        const int i = base + threadIdx.x;
+        int v = 0, keep = 0;
+        if (i < pl.budget) {
+            v = linspace_index(pl.lin_start, pl.lin_end, pl.lin_step, pl.budget, i);
+            keep = i == 0 || v != linspace_index(pl.lin_start, pl.lin_end, pl.lin_step, pl.budget, i - 1);
+        }
+        int incl = keep;  // inclusive scan of `keep` over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += n; }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int pos = carry + (warp ? warp_sum[warp - 1] : 0) + incl - keep;
+        if (keep && pos < pl.n_old) table[pos] = v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sum[31];
+        __syncthreads();
+    }
+}
+} }
+
+extern "C" int kvq_evict_old_table_device(const kvq_evict_plan* plan, int32_t* old_table, kvq_stream_t stream) {
+    KVQ_REQUIRE(plan && old_table, "null pointer");
+    KVQ_REQUIRE(plan->strategy == KVQ_EVICT_BUDGET && plan->budget > 0, "old_table exists for budget plans with old_len > budget only");
+    const PlanDev d = to_dev(*plan, false);
+    budget_table_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d, old_table);
+    return check_launch("evict_old_table");
 }
 
 // ------------------------------------------------------------------------------------------------ paged store
@@ -393,9 +471,41 @@ extern "C" int kvq_paged_gather(const void* pool, int elem_bytes, const int64_t 
     return check_launch("paged_gather");
 }
 
-// One token is B*H rows of D elements (<= a few tens of KB): a single element-wise kernel; the block
-// table lookup for the one logical block is done by the device (table stays resident on the GPU).
+// n tokens of B*H rows each.  Fast path: one 16-byte vector per thread, 4 in flight, 32-bit index arithmetic
+// (row -> (plane, token) costs one division per VECTOR, not four 64-bit div/mod per element); the block-table lookup is
+// done by the device (the table stays resident on the GPU).
 namespace kvq { namespace {
+struct AppendGeom {
+    int nP, H, N, cpr, block;     // planes, heads, tokens appended, 16-byte chunks per row, tokens per block
+    int64_t sB, sH, sT;           // source strides in BYTES
+    int64_t plane_bytes, block_bytes, row_bytes;
+    int64_t t;                    // logical position of the first appended token
+};
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads) paged_append_vec_kernel(const char* __restrict__ x, char* __restrict__ pool, AppendGeom g,
+                                                                   const int32_t* __restrict__ table) {
+    const unsigned n_vec = (unsigned)g.nP * g.N * g.cpr;
+    const unsigned i0 = (blockIdx.x * UNROLL) * kThreads + threadIdx.x;
+    uint4 v[UNROLL];
+    char* dst[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const unsigned i = i0 + u * kThreads;
+        dst[u] = nullptr;
+        if (i < n_vec) {
+            const unsigned r = i / g.cpr, c = i - r * g.cpr;   // r = p * N + j
+            const unsigned p = r / g.N, j = r - p * g.N;
+            const unsigned b = g.H == 1 ? p : p / g.H, h = p - b * g.H;
+            const int64_t lt = g.t + j, lb = lt / g.block, slot = lt - lb * g.block;
+            v[u] = ld_stream(x + b * g.sB + h * g.sH + (int64_t)j * g.sT + (int64_t)c * 16);
+            dst[u] = pool + (int64_t)__ldg(table + lb) * g.block_bytes + (int64_t)p * g.plane_bytes + slot * g.row_bytes + (int64_t)c * 16;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+        if (dst[u]) st_stream(dst[u], v[u]);
+}
+
 // n tokens starting at logical position t (n == 1: the reference's per-token append; n > 1: a whole prompt in one launch)
 template <typename E>
 __global__ void __launch_bounds__(kThreads) paged_append_tbl_kernel(const E* __restrict__ x, E* __restrict__ pool, int64_t B,
@@ -420,6 +530,21 @@ extern "C" int kvq_paged_append(const void* x, int elem_bytes, const int64_t sha
     const int64_t B = shape[0], H = shape[1], N = shape[2], D = shape[3];
     if (B * H * D == 0) return KVQ_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rb = D * elem_bytes;
+    auto a16 = [&](int64_t s_) { return (s_ * elem_bytes) % 16 == 0; };
+    if (stride[3] == 1 && rb % 16 == 0 && aligned16(x) && aligned16(pool) && a16(stride[0]) && a16(stride[1]) && a16(stride[2]) &&
+        B * H * N * (rb / 16) < 0x7fffffffLL && block_size <= 0x7fffffff) {
+        AppendGeom g{(int)(B * H), (int)H, (int)N, (int)(rb / 16), (int)block_size, stride[0] * elem_bytes, stride[1] * elem_bytes,
+                     stride[2] * elem_bytes, block_size * rb, B * H * block_size * rb, rb, t};
+        if (B == 1) { g.H = 1; g.sB = g.sH; }
+        else if (H == 1) { g.H = 1; }
+        else if (stride[0] == H * stride[1]) { g.H = 1; g.sB = g.sH; }
+        constexpr int U = 4;
+        const int64_t n_vec = B * H * N * (rb / 16);
+        const unsigned grid = (unsigned)((n_vec + kThreads * U - 1) / (kThreads * U));
+        paged_append_vec_kernel<U><<<grid, kThreads, 0, st>>>((const char*)x, (char*)pool, g, block_table);
+        return check_launch("paged_append");
+    }
     const unsigned grid = gen_grid(B * H * N * D);
 #define KVQ_PA(E) paged_append_tbl_kernel<E><<<grid, kThreads, 0, st>>>((const E*)x, (E*)pool, B, H, N, D, stride[0], stride[1], stride[2], \
                                                                         stride[3], block_size, block_table, t)

@@ -62,8 +62,11 @@ template <int DT> struct Acc {
 };
 
 template <int DT>
-__global__ void __launch_bounds__(kThreads) chunk_mean_kernel(const char* __restrict__ x, char* __restrict__ out, PoolGeom g) {
+__global__ void __launch_bounds__(kThreads) chunk_mean_kernel(const char* __restrict__ x, char* __restrict__ out, PoolGeom g,
+                                                             const void* const* __restrict__ xs = nullptr,
+                                                             void* const* __restrict__ outs = nullptr) {
     constexpr int ES = ElemT<DT>::kSize;
+    if (xs) { x = reinterpret_cast<const char*>(xs[blockIdx.z]); out = reinterpret_cast<char*>(outs[blockIdx.z]); }  // batched: z = tensor
     constexpr int kInFlight = 8;
     const int c = threadIdx.x % g.cpr, r0 = threadIdx.x / g.cpr, rpp = kThreads / g.cpr;
     if (r0 >= rpp) return;
@@ -122,9 +125,9 @@ __global__ void __launch_bounds__(kThreads) chunk_mean_generic_kernel(const void
 
 using namespace kvq;
 
-extern "C" int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int64_t chunk,
-                              int64_t keep_last, void* out, kvq_stream_t stream) {
-    KVQ_REQUIRE(x && out && shape && stride, "null pointer");
+namespace kvq { namespace {
+int run_chunk_mean(const void* x, void* out, const void* const* xs, void* const* outs, int64_t n_tensors, bool ptrs_aligned, int dtype,
+                   const int64_t shape[4], const int64_t stride[4], int64_t chunk, int64_t keep_last, cudaStream_t st) {
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     KVQ_REQUIRE(chunk >= 1 && chunk <= 0x7fffffff, "chunk_size must be >= 1");
     KVQ_REQUIRE(keep_last >= 0, "keep_last must be >= 0");
@@ -133,23 +136,24 @@ extern "C" int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], 
     const int64_t keep_eff = keep_last < T ? keep_last : T, old_len = T - keep_eff;
     KVQ_REQUIRE(old_len > 0, "nothing to summarise (T <= keep_last): the caller returns the cache unchanged (implementations.py:316-318)");
     const int64_t n_chunks = (old_len + chunk - 1) / chunk, Tn = n_chunks + keep_eff;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (B * H * D == 0) return KVQ_OK;
+    if (B * H * D == 0 || n_tensors == 0) return KVQ_OK;
     const int es = elem_size(dtype);
     const int64_t rb = D * es;
     auto a16 = [&](int64_t s) { return (s * es) % 16 == 0; };
-    const bool fast = stride[3] == 1 && rb % 16 == 0 && rb / 16 <= kThreads && aligned16(x) && aligned16(out) && a16(stride[0]) &&
+    const bool fast = stride[3] == 1 && rb % 16 == 0 && rb / 16 <= kThreads && ptrs_aligned && a16(stride[0]) &&
                       a16(stride[1]) && a16(stride[2]);
     if (fast) {
         PoolGeom g{(int)(B * H), (int)H, stride[0], stride[1], stride[2], T, old_len, n_chunks, keep_eff, Tn, (int)chunk, (int)(rb / 16)};
         const int rpp = kThreads / g.cpr;
-        dim3 grid((unsigned)((Tn + rpp - 1) / rpp), (unsigned)(g.nP < 65535 ? g.nP : 65535));
+        dim3 grid((unsigned)((Tn + rpp - 1) / rpp), (unsigned)(g.nP < 65535 ? g.nP : 65535), (unsigned)n_tensors);
         switch (dtype) {
-            case KVQ_F32: chunk_mean_kernel<KVQ_F32><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g); break;
-            case KVQ_F16: chunk_mean_kernel<KVQ_F16><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g); break;
-            default: chunk_mean_kernel<KVQ_BF16><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g); break;
+            case KVQ_F32: chunk_mean_kernel<KVQ_F32><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g, xs, outs); break;
+            case KVQ_F16: chunk_mean_kernel<KVQ_F16><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g, xs, outs); break;
+            default: chunk_mean_kernel<KVQ_BF16><<<grid, kThreads, 0, st>>>((const char*)x, (char*)out, g, xs, outs); break;
         }
     } else {
+        if (xs) return fail(KVQ_ERR_UNSUPPORTED, "chunk_mean_batched: rows must be 16-byte multiples with 16-byte-aligned strides and pointers "
+                                                 "(use kvq_chunk_mean per tensor for other layouts)");
         const int64_t n = B * H * Tn * D;
         const int64_t blocks = (n + kThreads - 1) / kThreads, cap = (int64_t)sm_count() * 32;
         const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
@@ -163,4 +167,19 @@ extern "C" int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], 
 #undef KVQ_CM
     }
     return check_launch("chunk_mean");
+}
+} }
+
+extern "C" int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int64_t chunk,
+                              int64_t keep_last, void* out, kvq_stream_t stream) {
+    KVQ_REQUIRE(x && out && shape && stride, "null pointer");
+    return run_chunk_mean(x, out, nullptr, nullptr, 1, aligned16(x) && aligned16(out), dtype, shape, stride, chunk, keep_last,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int kvq_chunk_mean_batched(const void* const* xs, void* const* outs, int64_t n_tensors, int dtype, const int64_t shape[4],
+                                      const int64_t stride[4], int64_t chunk, int64_t keep_last, kvq_stream_t stream) {
+    KVQ_REQUIRE(xs && outs && shape && stride, "null pointer");
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535, "n_tensors out of range");
+    return run_chunk_mean(nullptr, nullptr, xs, outs, n_tensors, true, dtype, shape, stride, chunk, keep_last, (cudaStream_t)stream);
 }

@@ -40,7 +40,8 @@ struct Scale {
 
 template <int BITS> __device__ __forceinline__ Scale scale_from_bits(uint32_t absmax_bits, float eps) {
     Scale sc;
-    sc.s = fmaxf(__fdiv_rn(__uint_as_float(absmax_bits), Q<BITS>::qmax), eps);
+    const float a = __fdiv_rn(__uint_as_float(absmax_bits), Q<BITS>::qmax);
+    sc.s = a != a ? a : fmaxf(a, eps);  // clamp(min=eps) propagates NaN (torch semantics); fmaxf alone would return eps
     sc.y = __frcp_rn(sc.s);
     return sc;
 }
@@ -49,9 +50,12 @@ template <int BITS> __device__ __forceinline__ Scale scale_from_bits(uint32_t ab
 // (BITS=4) is code+8.
 // CLAMP = false: the caller guarantees max|x| <= the absmax the scale came from (it is the phase-1 result of this
 // very data, possibly max-combined with other shards), so |x/scale| <= qmax * (1 + 2^-23) and the clamp is dead code.
-template <int DT, int BITS, bool CLAMP = true> __device__ __forceinline__ uint32_t code_word(float x, const Scale& sc) {
+// TRUE_DIV: IEEE division also for 16-bit inputs.  The division-free quotient is proved exact (by exhaustion) for scales that
+// are absmax / qmax of a 16-bit-representable absmax or the default eps; callers that pass a calibrated fp32 absmax or a
+// custom eps get the division.
+template <int DT, int BITS, bool CLAMP = true, bool TRUE_DIV = false> __device__ __forceinline__ uint32_t code_word(float x, const Scale& sc) {
     float q;
-    if (DT == KVQ_F32) {
+    if (DT == KVQ_F32 || TRUE_DIV) {
         q = __fdiv_rn(x, sc.s);
     } else {
         const float q0 = __fmul_rn(x, sc.y);
@@ -100,21 +104,21 @@ template <int DT> struct InVec {
 };
 
 // codes of one input vector, stored at `out` (naturally aligned): kN bytes (INT8) or kN/2 bytes (INT4)
-template <int DT, int BITS, bool CLAMP = true> __device__ __forceinline__ void quant_store(const uint4& v, const Scale& sc, void* out) {
+template <int DT, int BITS, bool CLAMP = true, bool TRUE_DIV = false> __device__ __forceinline__ void quant_store(const uint4& v, const Scale& sc, void* out) {
     constexpr int kN = InVec<DT>::kN;
     float f[kN];
     InVec<DT>::widen(v, f);
     if constexpr (BITS == 8) {
         uint32_t c[kN];
 #pragma unroll
-        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8, CLAMP>(f[i], sc);
+        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8, CLAMP, TRUE_DIV>(f[i], sc);
         if constexpr (kN == 8) st_stream8(out, make_uint2(pack4_bytes(c[0], c[1], c[2], c[3]), pack4_bytes(c[4], c[5], c[6], c[7])));
         else st_stream4(out, pack4_bytes(c[0], c[1], c[2], c[3]));
     } else {
         uint32_t b[kN / 2];
 #pragma unroll
         for (int i = 0; i < kN / 2; ++i)
-            b[i] = code_word<DT, 4, CLAMP>(f[2 * i], sc) * 16u + code_word<DT, 4, CLAMP>(f[2 * i + 1], sc);  // low byte valid
+            b[i] = code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i], sc) * 16u + code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i + 1], sc);  // low byte valid
         if constexpr (kN == 8) st_stream4(out, pack4_bytes(b[0], b[1], b[2], b[3]));
         else *reinterpret_cast<unsigned short*>(out) = (unsigned short)(__byte_perm(b[0], b[1], 0x0040) & 0xffffu);
     }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __res
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t j = i + (int64_t)u * kThreads;
-            if (j < n_vec) quant_store<DT, BITS, CLAMP>(v[u], sc, qt + j * kOut);
+            if (j < n_vec) quant_store<DT, BITS, CLAMP, CLAMP>(v[u], sc, qt + j * kOut);
         }
     }
 }
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __rest
                 for (int u = 0; u < UNROLL; ++u) {
                     if (tb + r0 + u * rpp >= g.T) continue;
                     if (per_token) { const float2 s2 = tile_scale[r0 + u * rpp]; sc.s = s2.x; sc.y = s2.y; }
-                    quant_store<DT, BITS, CLAMP>(v[u], sc, qout + u * out_step);
+                    quant_store<DT, BITS, CLAMP, CLAMP>(v[u], sc, qout + u * out_step);
                 }
             }
         }
@@ -317,12 +321,27 @@ __global__ void __launch_bounds__(kThreads) quant_rows_kernel(const char* __rest
 // NV == 0: any size; two loops over the token, the second one hits L2.
 // MODE 0: quantize (+ scales, + absmax out); MODE 1: absmax only (phase 1 of the head-sharded path).
 
+// Batched form (tb.xs != nullptr): blockIdx.y is the tensor -- all layers' K (or V) streams of a step share shape, strides and
+// bit width; destination rows start `row_off` tokens into every store (QuantizedKVCache.append_from_past /
+// init_from_prompt_past loop `for layer: quantize(k); quantize(v)`, ops.py:323-342: 2L launches -> one per bit width).
+struct TokBatch {
+    const void* const* xs; void* const* qs; void* const* scales; float* const* scales_f32;
+    int64_t row_off;  // tokens
+};
+
 template <int DT, int BITS, int NV, int MODE>
 __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __restrict__ x, RowGeom g, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out,
-                                                              uint32_t* __restrict__ absmax_out, int accumulate) {
+                                                              uint32_t* __restrict__ absmax_out, int accumulate,
+                                                              TokBatch tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
     __shared__ uint32_t red[kThreads / 32];
+    if (tb.xs) {
+        x = reinterpret_cast<const char*>(tb.xs[blockIdx.y]);
+        q = reinterpret_cast<char*>(tb.qs[blockIdx.y]) + tb.row_off * g.qT;
+        scale_out = tb.scales ? reinterpret_cast<char*>(tb.scales[blockIdx.y]) + tb.row_off * ElemT<DT>::kSize : nullptr;
+        scale_f32_out = tb.scales_f32 ? tb.scales_f32[blockIdx.y] + tb.row_off : nullptr;
+    }
     constexpr int kOut = OutBytes<DT, BITS>::value;
     constexpr int kNV = NV > 0 ? NV : 1;
     // The max is taken over this very data, so the clamp can never bind (see code_word).  Whether the two dead FMNMX
@@ -437,10 +456,10 @@ __global__ void __launch_bounds__(kThreads) quant_generic_kernel(const void* __r
         const int64_t xrow = b * g.xB + h * g.xH + t * g.xT;
         uint8_t* out = reinterpret_cast<uint8_t*>(q) + b * g.qB + h * g.qH + t * g.qT + j;
         if (BITS == 8) {
-            *out = (uint8_t)(code_word<DT, 8>(load_as_float<DT>(x, xrow + j * g.xD), sc) & 0xffu);
+            *out = (uint8_t)(code_word<DT, 8, true, true>(load_as_float<DT>(x, xrow + j * g.xD), sc) & 0xffu);
         } else {
-            const uint32_t hi = code_word<DT, 4>(load_as_float<DT>(x, xrow + 2 * j * g.xD), sc) & 0xfu;
-            const uint32_t lo = (2 * j + 1 < g.D) ? (code_word<DT, 4>(load_as_float<DT>(x, xrow + (2 * j + 1) * g.xD), sc) & 0xfu) : 8u;
+            const uint32_t hi = code_word<DT, 4, true, true>(load_as_float<DT>(x, xrow + 2 * j * g.xD), sc) & 0xfu;
+            const uint32_t lo = (2 * j + 1 < g.D) ? (code_word<DT, 4, true, true>(load_as_float<DT>(x, xrow + (2 * j + 1) * g.xD), sc) & 0xfu) : 8u;
             *out = (uint8_t)((hi << 4) | lo);
         }
     }
@@ -706,13 +725,34 @@ RowGeom row_geom(const View4& v, int es, const Stride3& q, int qes, int vpr) {
     return g;
 }
 
-// grid sizes of the strided-row and per-token kernels, in CTAs per SM (KVQ_ROWS_CTAS_PER_SM / KVQ_TOKEN_CTAS_PER_SM: tuning knobs)
-int env_int(const char* name, int dflt) { const char* e = getenv(name); const int n = e ? atoi(e) : 0; return n > 0 ? n : dflt; }
+// grid sizes of the strided-row and per-token kernels, in CTAs per SM
+// (compile-time constants: -DKVQ_..._CTAS_PER_SM=n rebuilds for a sweep; a library does not read tuning knobs from the environment)
+#ifndef KVQ_QROWS_CTAS_PER_SM
+#define KVQ_QROWS_CTAS_PER_SM 32
+#endif
+#ifndef KVQ_ROWS_CTAS_PER_SM
+#define KVQ_ROWS_CTAS_PER_SM 128
+#endif
+#ifndef KVQ_TOKEN_CTAS_PER_SM
+#define KVQ_TOKEN_CTAS_PER_SM 32
+#endif
+#ifndef KVQ_FLAT_MODE_ABSMAX
+#define KVQ_FLAT_MODE_ABSMAX -128
+#endif
+#ifndef KVQ_FLAT_MODE_QUANT
+#define KVQ_FLAT_MODE_QUANT -128
+#endif
+#ifndef KVQ_FLAT_MODE_DEQUANT
+#define KVQ_FLAT_MODE_DEQUANT 1
+#endif
+#ifndef KVQ_FLAT_MIN_CPC
+#define KVQ_FLAT_MIN_CPC 3
+#endif
 // measured on B200 (profiles/r1c_grid_sweep.log): many short CTAs beat a few persistent ones here too; the quantize rows
 // kernel (two block barriers per tile) peaks at 32 per SM, the barrier-free dequantize / absmax rows kernels at 128
-int quant_rows_ctas_per_sm() { static const int v = env_int("KVQ_QROWS_CTAS_PER_SM", 32); return v; }
-int rows_ctas_per_sm() { static const int v = env_int("KVQ_ROWS_CTAS_PER_SM", 128); return v; }
-int token_ctas_per_sm() { static const int v = env_int("KVQ_TOKEN_CTAS_PER_SM", 32); return v; }
+constexpr int quant_rows_ctas_per_sm() { return KVQ_QROWS_CTAS_PER_SM; }
+constexpr int rows_ctas_per_sm() { return KVQ_ROWS_CTAS_PER_SM; }
+constexpr int token_ctas_per_sm() { return KVQ_TOKEN_CTAS_PER_SM; }
 
 // planes are looped inside the CTA (the per-tile scales are reused): y covers at most 8 plane groups
 dim3 row_grid_planes_inside(const RowGeom& g, int unroll) {
@@ -735,20 +775,11 @@ dim3 row_grid(const RowGeom& g, int unroll) {
     return dim3((unsigned)(gx > 0 ? gx : 1), gy, 1);
 }
 // Work split of the flat kernels per kernel kind (0 absmax, 1 quantize, 2 dequantize).  v > 0: v consecutive chunks per CTA;
-// v < 0: |v| CTAs per SM per tensor, each striding over the tensor.  KVQ_FLAT_MODE="a,q,d" overrides (tuning knob).
+// v < 0: |v| CTAs per SM per tensor, each striding over the tensor.  -DKVQ_FLAT_MODE_{ABSMAX,QUANT,DEQUANT}=v overrides at build time.
 // Measured on B200 with 1 GiB bf16 tensors (profiles/r1c_grid_sweep.log): the write-heavy dequantize stream wants one
 // 16 KB chunk per CTA (6.6 TB/s vs 5.5 with 16 persistent CTAs per SM), the issue-bound quantize and the read-only absmax
 // want ~128 short CTAs per SM.
-int flat_mode(int kind) {
-    static int v[3] = {0, 0, 0};
-    static const bool init = [] {
-        v[0] = -128; v[1] = -128; v[2] = 1;
-        if (const char* e = getenv("KVQ_FLAT_MODE")) { int a = 0, q = 0, d = 0; if (sscanf(e, "%d,%d,%d", &a, &q, &d) == 3 && a && q && d) { v[0] = a; v[1] = q; v[2] = d; } }
-        return true;
-    }();
-    (void)init;
-    return v[kind];
-}
+constexpr int flat_mode(int kind) { return kind == 0 ? KVQ_FLAT_MODE_ABSMAX : kind == 1 ? KVQ_FLAT_MODE_QUANT : KVQ_FLAT_MODE_DEQUANT; }
 void flat_work(int64_t n_vec, int unroll, int kind, int64_t n_tensors, FlatWork& w, unsigned& grid) {
     const int64_t per = (int64_t)kThreads * unroll;
     w.chunks = (n_vec + per - 1) / per;
@@ -759,7 +790,7 @@ void flat_work(int64_t n_vec, int unroll, int kind, int64_t n_tensors, FlatWork&
         bpt = (int64_t)sm_count() * -mode;
         // small tensors (a head shard at N = 8 is 128 MB): keep ~3 strided chunks per CTA rather than degenerating into one chunk
         // per CTA, which costs the issue-bound quantize kernel 15-20 % (profiles/r1c_grid_sweep.log, table 2 row cpc = 1)
-        static const int min_cpc = env_int("KVQ_FLAT_MIN_CPC", 3);
+        constexpr int min_cpc = KVQ_FLAT_MIN_CPC;
         if (kind != 2 && min_cpc > 1 && bpt * min_cpc > w.chunks) bpt = (w.chunks + min_cpc - 1) / min_cpc;
         if (bpt > w.chunks) bpt = w.chunks;
         if (bpt > max_bpt) bpt = max_bpt;
@@ -800,7 +831,8 @@ int quant_phase2(const void* x, int dtype, const int64_t shape[4], const int64_t
                  const uint32_t* absmax_bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
                  float* scale_f32_out, cudaStream_t st) {
     KVQ_REQUIRE(x && q && absmax_bits && shape && stride, "null pointer");
-    const bool covers = (granularity & KVQ_ABSMAX_COVERS_INPUT) != 0;
+    // the clamp-free, division-free instantiation is proved exact for the phase-1 absmax of this very data and the default eps only
+    const bool covers = (granularity & KVQ_ABSMAX_COVERS_INPUT) != 0 && eps == 1e-8f;
     granularity &= ~KVQ_ABSMAX_COVERS_INPUT;
     KVQ_REQUIRE(granularity == KVQ_PER_TENSOR || granularity == KVQ_PER_TOKEN, "bad granularity %d", granularity);
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
@@ -916,9 +948,10 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
 }
 
 template <int DT, int BITS, int MODE>
-void launch_token_fused(int nv, unsigned grid, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
-                        void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate) {
-#define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate)
+void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
+                        void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate,
+                        const TokBatch& tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
+#define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
     if (nv <= 1) KVQ_TF(1);
     else if (nv <= 2) KVQ_TF(2);
     else if (nv <= 4) KVQ_TF(4);
@@ -927,9 +960,9 @@ void launch_token_fused(int nv, unsigned grid, cudaStream_t st, const void* x, c
 #undef KVQ_TF
 }
 
-unsigned token_grid(int64_t T) {
+dim3 token_grid(int64_t T) {
     const int64_t cap = (int64_t)sm_count() * token_ctas_per_sm();
-    return (unsigned)(T < cap ? T : cap);
+    return dim3((unsigned)(T < cap ? T : cap));
 }
 
 }  // namespace
@@ -1008,7 +1041,8 @@ extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t
     const int es = elem_size(dtype);
     const int piece = (16 / es) * bits / 8;
     const int64_t n_vec = v.B * v.H * (v.D * es / 16);
-    if (fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece) && n_vec < (1 << 30) && (bits == 8 || v.D % 2 == 0)) {
+    // (a custom eps takes the two-phase path below: its quantize kernels divide exactly, see code_word)
+    if (eps == 1e-8f && fast_input_ok(x, dtype, v) && codes_ok(q, qs, piece) && n_vec < (1 << 30) && (bits == 8 || v.D % 2 == 0)) {
         const RowGeom g = row_geom(v, es, qs, 1, (int)(v.D * es / 16));
         int nv = (int)((n_vec + kThreads - 1) / kThreads);
         const int64_t xmax = ((v.B - 1) * v.sB + (v.H - 1) * v.sH + v.D) * es, qmaxo = (v.B - 1) * qs.sB + (v.H - 1) * qs.sH + W;
@@ -1032,6 +1066,45 @@ extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t
                                scale_f32_out, st);
     return quant_phase2<4>(x, dtype, shape, stride, KVQ_PER_TOKEN, absmax_bits_out, eps, q, q_stride3, scale_out,
                            scale_f32_out, st);
+}
+
+extern "C" int kvq_quant_per_token_fused_batched(const void* const* xs, int dtype, int64_t n_tensors, const int64_t shape[4],
+                                                 const int64_t stride[4], int bits, float eps, void* const* qs,
+                                                 const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
+                                                 float* const* scales_f32_out, kvq_stream_t stream) {
+    KVQ_REQUIRE(xs && qs && shape && stride, "null pointer");
+    KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4, got %d", bits);
+    KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
+    KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && dst_token_offset >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const View4 v = make_view(shape, stride);
+    KVQ_REQUIRE(v.B >= 0 && v.H >= 0 && v.T >= 0 && v.D >= 0, "negative shape");
+    const int64_t W = bits == 8 ? v.D : (v.D + 1) / 2;
+    const Stride3 qst = make_stride3(q_stride3, v.H, v.T, W);
+    if (v.B * v.H * v.T * v.D == 0 || n_tensors == 0) return KVQ_OK;
+    const int es = elem_size(dtype);
+    const int piece = (16 / es) * bits / 8;
+    const int64_t n_vec = v.B * v.H * (v.D * es / 16);
+    // (pointer alignment is the caller's promise here: the tables live on the device)
+    if (!(eps == 1e-8f && fast_input_ok(reinterpret_cast<const void*>(uintptr_t(16)), dtype, v) && codes_ok(reinterpret_cast<const void*>(uintptr_t(16)), qst, piece) &&
+          n_vec < (1 << 30) && (bits == 8 || v.D % 2 == 0)))
+        return fail(KVQ_ERR_UNSUPPORTED, "quant_per_token_fused_batched: needs the default eps and rows of 16-byte multiples with 16-byte-aligned strides "
+                                         "(use kvq_quant_per_token_fused per tensor for other layouts)");
+    const RowGeom g = row_geom(v, es, qst, 1, (int)(v.D * es / 16));
+    int nv = (int)((n_vec + kThreads - 1) / kThreads);
+    const int64_t xmax = ((v.B - 1) * v.sB + (v.H - 1) * v.sH + v.D) * es, qmaxo = (v.B - 1) * qst.sB + (v.H - 1) * qst.sH + W;
+    if (xmax >= 0xffffffffLL || qmaxo >= 0xffffffffLL || xmax < 0 || qmaxo < 0) nv = 9;
+    const TokBatch tb{xs, qs, scales_out, scales_f32_out, dst_token_offset};
+    int64_t gx = ((int64_t)sm_count() * token_ctas_per_sm() + n_tensors - 1) / n_tensors;
+    if (gx > v.T) gx = v.T;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)n_tensors);
+    if (bits == 8) {
+        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb));
+    } else {
+        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb));
+    }
+    return check_launch("quant_per_token_fused_batched");
 }
 
 extern "C" int kvq_dequant_int8(const int8_t* q, const int64_t shape[4], const int64_t q_stride3[3], const void* scale,
@@ -1074,7 +1147,7 @@ extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_ten
                                  kvq_stream_t stream) {
     KVQ_REQUIRE(xs && qs && absmax_bits, "null pointer");
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
-    const bool covers = (bits & KVQ_ABSMAX_COVERS_INPUT) != 0;
+    const bool covers = (bits & KVQ_ABSMAX_COVERS_INPUT) != 0 && eps == 1e-8f;
     bits &= ~KVQ_ABSMAX_COVERS_INPUT;
     KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4");
     KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");

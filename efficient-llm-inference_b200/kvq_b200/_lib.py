@@ -57,6 +57,10 @@ SIGNATURES = {
     "kvq_absmax_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     "kvq_quant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp]),
     "kvq_dequant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
+    "kvq_quant_per_token_fused_batched": (c_int, [c_vp, c_int, c_i64, I64x4, I64x4, c_int, c_f, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "kvq_evict_gather_batched": (c_int, [c_vp, c_vp, c_i64, c_int, I64x4, I64x4, ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),
+    "kvq_evict_old_table_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp]),
+    "kvq_chunk_mean_batched": (c_int, [c_vp, c_vp, c_i64, c_int, I64x4, I64x4, c_i64, c_i64, c_vp]),
     "kvq_evict_plan_make": (c_int, [c_int] + [c_i64] * 7 + [ctypes.POINTER(EvictPlan)]),
     "kvq_evict_indices_host": (c_int, [ctypes.POINTER(EvictPlan), c_vp]),
     "kvq_evict_indices_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),
@@ -163,6 +167,21 @@ def stride3(t4: torch.Tensor) -> ctypes.Array:
     if t4.size(-1) > 1 and t4.stride(-1) != 1:
         raise RuntimeError("code / output tensors need a contiguous last dimension")
     return I64x3(*t4.stride()[:3])
+
+
+def ptr_table(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Device int64 array of the data pointers of `tensors` (one small H2D copy): the argument of the *_batched entry points."""
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(tensors[0].device, non_blocking=True)
+
+
+def same_layout(tensors: Sequence[torch.Tensor]) -> bool:
+    """True when the tensors can share one batched launch: same shape / stride / dtype / device, 16-byte-aligned pointers."""
+    t0 = tensors[0]
+    sh, st, dt, dev = t0.shape, t0.stride(), t0.dtype, t0.device
+    for t in tensors:
+        if t.shape != sh or t.stride() != st or t.dtype != dt or t.device != dev or t.data_ptr() % 16:
+            return False
+    return True
 
 
 _NO_GUARD = contextlib.nullcontext()

@@ -43,12 +43,16 @@ def kept_token_indices(plan: L.EvictPlan) -> List[int]:
 
 
 def _old_table(plan: L.EvictPlan, device) -> Optional[torch.Tensor]:
-    """Only when float32 linspace produced duplicates (plan.needs_table): the older region's tokens."""
+    """Only when float32 linspace produced duplicates (plan.needs_table): the older region's tokens, built on the device
+    (linspace -> trunc -> unique_consecutive as one kernel; the indices never exist on the host)."""
     if not plan.needs_table:
         return None
-    idx = kept_token_indices(plan)
-    old = idx[plan.n_prefix: plan.n_prefix + plan.n_old]
-    return torch.tensor(old, dtype=torch.int32, device=device)
+    table = torch.empty(int(plan.n_old), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        L.check(L.lib().kvq_evict_old_table_device(ctypes.byref(plan), table.data_ptr(), L.stream_ptr(table.device)),
+                "kvq_evict_old_table_device")
+        L.count_launch()
+    return table
 
 
 def gather_tokens(x: torch.Tensor, plan: L.EvictPlan, table: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -72,18 +76,53 @@ def gather_tokens(x: torch.Tensor, plan: L.EvictPlan, table: Optional[torch.Tens
     return out
 
 
+def gather_tokens_batched(xs: List[torch.Tensor], plan: L.EvictPlan, table: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    """gather_tokens for n same-layout tensors (all layers x {K, V}) in ONE launch; returns views of one [n,B,H,kept,D] buffer."""
+    x0 = xs[0]
+    B, H, T, D = x0.shape
+    out = torch.empty((len(xs), B, H, int(plan.n_total), D), dtype=x0.dtype, device=x0.device)
+    outs = list(out.unbind(0))
+    if out.numel() == 0:
+        return outs
+    if table is None:
+        table = _old_table(plan, x0.device)
+    with L.device_guard(x0):
+        sh, st = L.shape_stride(x0)
+        L.check(L.lib().kvq_evict_gather_batched(L.ptr_table(xs).data_ptr(), L.ptr_table(outs).data_ptr(), len(xs), x0.element_size(),
+                                                 sh, st, ctypes.byref(plan), table.data_ptr() if table is not None else None, None,
+                                                 L.stream_ptr(x0.device)), "kvq_evict_gather_batched")
+        L.count_launch()
+    return outs
+
+
+def _batchable(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.stride(3) == 1 and (x.size(3) * x.element_size()) % 16 == 0 and x.size(3) * x.element_size() <= 4096 and \
+        all((s * x.element_size()) % 16 == 0 for s in x.stride()[:3])
+
+
 def _trim(past_key_values, strategy: int, **params) -> tuple:
+    """All layers x {K, V} that share a layout go through ONE gather launch (the reference loops per layer and per tensor,
+    implementations.py:176-190, :218-245, :268-292); anything else one launch per tensor."""
+    pkv = list(past_key_values)
+    flat = [t for kv in pkv for t in kv]
+    if len(flat) > 2 and flat[0].is_cuda and _batchable(flat[0]) and L.same_layout(flat):
+        plan = evict_plan(strategy, flat[0].size(2), **params)
+        if plan.identity:
+            return tuple((k, v) for k, v in pkv)
+        outs = gather_tokens_batched(flat, plan)
+        return tuple((outs[2 * i], outs[2 * i + 1]) for i in range(len(pkv)))
     trimmed = []
     plans = {}
-    for k, v in past_key_values:
+    for k, v in pkv:
         T = k.size(2)
-        plan = plans.get(T)
-        if plan is None:
-            plan = plans[T] = evict_plan(strategy, T, **params)
+        ent = plans.get(T)
+        if ent is None:
+            plan = evict_plan(strategy, T, **params)
+            ent = plans[T] = (plan, None if plan.identity else _old_table(plan, k.device))
+        plan, table = ent
         if plan.identity:
             trimmed.append((k, v))
             continue
-        table = _old_table(plan, k.device)
         trimmed.append((gather_tokens(k, plan, table), gather_tokens(v, plan, table)))
     return tuple(trimmed)
 
@@ -151,9 +190,30 @@ def chunk_summarize_kv(past_key_values: tuple, chunk_size: int, keep_last: int) 
     """Replace all but the last keep_last tokens by mean-pooled chunk summaries; one fused launch per
     tensor (segmented mean + copy of the recent tokens).  The zero-padded last chunk is divided by
     chunk_size, like the reference."""
-    summarized = []
-    for k, v in past_key_values:
+    pkv = list(past_key_values)
+    for k, v in pkv:
         L.require_cuda(k, v)
+    flat = [t for kv in pkv for t in kv]
+    if len(flat) > 2 and _batchable(flat[0]) and L.same_layout(flat):  # one launch for all layers x {K, V}
+        x0 = flat[0]
+        B, H, T, D = x0.shape
+        keep_eff = min(keep_last, T)
+        old_len = T - keep_eff
+        if old_len <= 0:
+            return tuple((k, v) for k, v in pkv)
+        n_chunks = (old_len + chunk_size - 1) // chunk_size
+        out = torch.empty((len(flat), B, H, n_chunks + keep_eff, D), dtype=x0.dtype, device=x0.device)
+        outs = list(out.unbind(0))
+        if out.numel():
+            with L.device_guard(x0):
+                sh, st = L.shape_stride(x0)
+                L.check(L.lib().kvq_chunk_mean_batched(L.ptr_table(flat).data_ptr(), L.ptr_table(outs).data_ptr(), len(flat),
+                                                       L.dtype_code(x0.dtype), sh, st, int(chunk_size), int(keep_last),
+                                                       L.stream_ptr(x0.device)), "kvq_chunk_mean_batched")
+                L.count_launch()
+        return tuple((outs[2 * i], outs[2 * i + 1]) for i in range(len(pkv)))
+    summarized = []
+    for k, v in pkv:
         if k.size(2) - min(keep_last, k.size(2)) <= 0:
             summarized.append((k, v))
             continue

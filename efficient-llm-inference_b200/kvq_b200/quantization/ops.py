@@ -95,7 +95,9 @@ def _scale_arg(scale, device) -> torch.Tensor:
     L.require_cuda(scale)
     if scale.dtype not in L.DTYPE_CODE:
         scale = scale.float()
-    return scale.reshape(-1)[:1].contiguous() if scale.numel() >= 1 else scale
+    if scale.numel() != 1:
+        raise RuntimeError(f"per-tensor dequantize takes ONE scale, got a tensor of {scale.numel()} elements")
+    return scale.reshape(1)
 
 
 @torch.no_grad()
@@ -255,9 +257,9 @@ class _TokenStore:
         if self.start + need <= cap:
             return
         # out of room at the tail: move the live tokens to the front of a buffer that is large enough
-        new_cap = cap if 2 * need <= cap else max(cap, 1 << (need - 1).bit_length())
-        if new_cap == cap and need > cap:
-            new_cap = 1 << (need - 1).bit_length()
+        # (a window close to the capacity would otherwise re-copy the live store every cap - need steps: grow so that a copy
+        # is amortised over at least `need` appends)
+        new_cap = cap if 2 * need <= cap else max(cap, 2 << (need - 1).bit_length())
         codes = torch.empty((B, H, new_cap, W), dtype=self.codes.dtype, device=x.device)
         codes[:, :, : self.T].copy_(self.live_codes())
         scales = torch.empty(new_cap, dtype=self.scales.dtype, device=x.device)
@@ -299,6 +301,35 @@ class _TokenStore:
             L.count_launch()
         self.T += n
         self.n_scale_entries += n
+
+    @staticmethod
+    def append_per_token_batched(stores: "List[_TokenStore]", xs: List[torch.Tensor], eps: float = 1e-8) -> bool:
+        """append_per_token for n stores of the same bit width in ONE launch (kvq_quant_per_token_fused_batched).  Returns
+        False -- nothing done -- when the stores / inputs do not share a layout; the caller then loops."""
+        if len(stores) < 2 or not L.same_layout(xs):
+            return False
+        x0 = xs[0]
+        n = x0.size(2)
+        if x0.stride(3) != 1 or (x0.size(3) * x0.element_size()) % 16 or any((s * x0.element_size()) % 16 for s in x0.stride()[:3]):
+            return False
+        for st_, x in zip(stores, xs):
+            st_._reserve(x, n)
+        s0 = stores[0]
+        lo, cs, bits = s0.start + s0.T, s0.codes.stride(), s0.bits
+        for st_ in stores:
+            if st_.bits != bits or st_.start + st_.T != lo or st_.codes.stride() != cs or st_.scales.dtype != x0.dtype:
+                return False
+        sh, st4 = L.shape_stride(x0)
+        L.check(L.lib().kvq_quant_per_token_fused_batched(
+            L.ptr_table(xs).data_ptr(), L.dtype_code(x0.dtype), len(xs), sh, st4, bits, float(eps),
+            L.ptr_table([s_.codes for s_ in stores]).data_ptr(), L.stride3(s0.codes), lo,
+            L.ptr_table([s_.scales for s_ in stores]).data_ptr(), L.ptr_table([s_.scales_f32 for s_ in stores]).data_ptr(),
+            L.stream_ptr(x0.device)), "kvq_quant_per_token_fused_batched")
+        L.count_launch()
+        for st_ in stores:
+            st_.T += n
+            st_.n_scale_entries += n
+        return True
 
     def append_shared_scale(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
         """The reference's append() given n > 1 tokens: ONE scale over the whole [B,H,n,D] block
@@ -562,16 +593,46 @@ class QuantizedKVCache:
         self.layers = [QuantizedLayerKV(mode=mode, device=device, compute_dtype=compute_dtype, group=group)
                        for _ in range(n_layers)]
 
+    def _append_all(self, ks: List[torch.Tensor], vs: List[torch.Tensor]) -> None:
+        """Per-token append of every layer's K and V: one launch per bit width for ALL layers when they share a layout
+        (the usual case), else one launch per tensor."""
+        layers = self.layers[: len(ks)]
+        if len(ks) > 1 and all(l.group is None for l in layers) and all(k.is_cuda and k.dim() == 4 and k.numel() for k in ks + vs):
+            with L.device_guard(ks[0]):
+                kst, vst = [l._k for l in layers], [l._v for l in layers]
+                if kst[0].bits == vst[0].bits and ks[0].shape == vs[0].shape:
+                    if _TokenStore.append_per_token_batched(kst + vst, ks + vs):
+                        return
+                else:
+                    done_k = _TokenStore.append_per_token_batched(kst, ks)
+                    done_v = _TokenStore.append_per_token_batched(vst, vs)
+                    if done_k and done_v:
+                        return
+                    for l, k, v in zip(layers, ks, vs):
+                        if not done_k:
+                            l._check_pair(k, v)
+                            l._k.append_per_token(k, group=None)
+                        if not done_v:
+                            l._check_pair(k, v)
+                            l._v.append_per_token(v, group=None)
+                    return
+        for l, k, v in zip(layers, ks, vs):
+            l.append_tokens(k, v)
+
     @torch.no_grad()
     def append_from_past(self, past_key_values: tuple) -> None:
         """Append the last token of every layer's (k, v)."""
-        for i, (k, v) in enumerate(past_key_values):
-            self.layers[i].append(k[:, :, -1:, :], v[:, :, -1:, :])
+        pkv = list(past_key_values)
+        self._append_all([k[:, :, -1:, :] for k, _ in pkv], [v[:, :, -1:, :] for _, v in pkv])
 
     @torch.no_grad()
     def init_from_prompt_past(self, past_key_values: tuple) -> None:
         """Quantize the whole prompt, one scale per token (the reference loops over t, ops.py:339-342)."""
-        for layer_idx, (k, v) in enumerate(past_key_values):
+        pkv = [(k, v) for k, v in past_key_values]
+        if all(k.size(2) > 0 for k, _ in pkv):
+            self._append_all([k for k, _ in pkv], [v for _, v in pkv])
+            return
+        for layer_idx, (k, v) in enumerate(pkv):
             if k.size(2) > 0:
                 self.layers[layer_idx].append_tokens(k, v)
 

@@ -153,6 +153,18 @@ KVQ_API int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_tensor
 KVQ_API int kvq_dequant_batched(const void* const* codes, int bits, int64_t n_tensors, int64_t numel, const void* scales,
                                 int scale_dtype, void* const* outs, int out_dtype, kvq_stream_t stream);
 
+/* Per-token single-pass quantize of n same-shape tensors (all layers' K streams, or all V streams, of a step) in ONE
+ * launch: tensor i is read from xs[i] ([B,H,T,D] with the common `stride`) and written to rows
+ * [dst_token_offset, dst_token_offset + T) of the store qs[i] (common q_stride3, bytes), its scales to
+ * scales_out[i][dst_token_offset + t] (x's dtype) and scales_f32_out[i][dst_token_offset + t].  xs / qs / scales_out /
+ * scales_f32_out are DEVICE arrays of n device pointers (the last two nullable); every pointer 16-byte aligned.
+ * KVQ_ERR_UNSUPPORTED for layouts the vector path cannot take (call kvq_quant_per_token_fused per tensor then).
+ * Replaces the loop `for layer: append(k[..., -1:, :], v[..., -1:, :])` / `for t: append(...)`, ops.py:323-342. */
+KVQ_API int kvq_quant_per_token_fused_batched(const void* const* xs, int dtype, int64_t n_tensors, const int64_t shape[4],
+                                              const int64_t stride[4], int bits, float eps, void* const* qs,
+                                              const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
+                                              float* const* scales_f32_out, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: eviction
  * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
  * of every destination row in registers; no index tensor and no intermediate parts list exists. */
@@ -198,6 +210,18 @@ KVQ_API int kvq_evict_gather(const void* src, int elem_bytes, const int64_t shap
                      const kvq_evict_plan* plan, const int32_t* old_table, void* dst,
                      const int64_t dst_stride3[3], kvq_stream_t stream);
 
+/* kvq_evict_gather for n same-shape tensors (all layers x {K, V} of a step) in ONE launch: srcs / dsts are DEVICE arrays
+ * of n device pointers, 16-byte aligned; shape, stride, plan and dst_stride3 are common.  The 256-320-row outputs of
+ * budget / prefix+window are latency-bound as separate launches; batched they stream.  KVQ_ERR_UNSUPPORTED for layouts
+ * the vector path cannot take.  Replaces the per-layer loops implementations.py:176-190, :218-245, :268-292. */
+KVQ_API int kvq_evict_gather_batched(const void* const* srcs, void* const* dsts, int64_t n_tensors, int elem_bytes,
+                                     const int64_t shape[4], const int64_t stride[4], const kvq_evict_plan* plan,
+                                     const int32_t* old_table, const int64_t dst_stride3[3], kvq_stream_t stream);
+
+/* Device: builds old_table (int32 [plan->n_old]) for a budget plan -- trunc(float32 linspace) with consecutive
+ * duplicates removed (implementations.py:279-282) -- so that the indices never exist on the host. */
+KVQ_API int kvq_evict_old_table_device(const kvq_evict_plan* plan, int32_t* old_table, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: paged store
  * Physical pool [n_blocks, B, H, block_size, D]; block_table[i] = physical block of logical block i.
  * The reference keeps a Python list of [B,H,block,D] tensors whose list index is the logical block
@@ -223,6 +247,11 @@ KVQ_API int kvq_paged_gather(const void* pool, int elem_bytes, const int64_t sha
  * Replaces: chunk_summarize_kv implementations.py:295-346 (pad-cat, view, mean, cat). */
 KVQ_API int kvq_chunk_mean(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4], int64_t chunk,
                    int64_t keep_last, void* out, kvq_stream_t stream);
+
+/* kvq_chunk_mean for n same-shape tensors in ONE launch (xs / outs: DEVICE arrays of n 16-byte-aligned device pointers).
+ * Replaces the per-layer loop implementations.py:316-346. */
+KVQ_API int kvq_chunk_mean_batched(const void* const* xs, void* const* outs, int64_t n_tensors, int dtype, const int64_t shape[4],
+                                   const int64_t stride[4], int64_t chunk, int64_t keep_last, kvq_stream_t stream);
 
 /* ---------------------------------------------------------------------------------- area 4: decode attention
  * One decode step over a per-token-quantized cache, dequantizing K/V in registers (split-K GEMV, no
