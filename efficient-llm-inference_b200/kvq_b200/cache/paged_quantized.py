@@ -190,6 +190,10 @@ class PagedQuantizedLayerKV:
             vc, vs = self._v.gather()
         return kc, ks, vc, vs
 
+    def length_after_sliding_window(self, window_size: int) -> int:
+        """len(self) after evict_sliding_window(window_size), without touching the store."""
+        return len(self) - max(0, (len(self) - int(window_size)) // self.block_size) * self.block_size
+
     def evict_sliding_window(self, window_size: int) -> int:
         """Keep at least the last `window_size` tokens by dropping whole leading blocks: a block-table edit, no data moves
         (block-granular version of trim_kv_to_window, implementations.py:124-141).  Returns the new length."""

@@ -21,6 +21,7 @@ Use `fused_attention(model)` as a context manager: it registers the attention fu
 from __future__ import annotations
 
 import contextlib
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -32,8 +33,29 @@ from .quantization.ops import QuantizedLayerKV
 
 ATTN_NAME = "kvq_fused"
 
-# the layer whose update() ran last, per layer index: the attention function of the same module call reads it
-_pending = {}
+# per host thread: layer index -> (cache layer, the key tensor its update() returned).  The attention function of the same
+# module call pops the entry and checks that the `key` it was handed IS that tensor, so two models (or two caches) in
+# flight can never read each other's layers.
+_tls = threading.local()
+
+
+def _pending() -> dict:
+    d = getattr(_tls, "pending", None)
+    if d is None:
+        d = _tls.pending = {}
+    return d
+
+
+def _mask_is_trivial(mask: Optional[torch.Tensor]) -> bool:
+    """True when `mask` lets the one query token see every key (None, all-True bool, all-zero additive).  The same mask
+    object serves every layer of a forward: the device sync is paid once per step, not once per layer."""
+    if mask is None:
+        return True
+    key = (mask.data_ptr(), tuple(mask.shape), mask._version)
+    if getattr(_tls, "mask_key", None) != key:
+        _tls.mask_key = key
+        _tls.mask_ok = bool(mask.all()) if mask.dtype == torch.bool else bool((mask == 0).all())
+    return _tls.mask_ok
 
 
 class KvqCacheLayer(CacheLayerMixin):
@@ -78,11 +100,19 @@ class KvqCacheLayer(CacheLayerMixin):
                 self.store.evict(**self.evict)
         self.cached_before_update = len(self.store)
         self.store.append_tokens(key_states, value_states)  # one scale per token, one launch per tensor
-        _pending[self.layer_idx] = self
+        _pending()[self.layer_idx] = (self, key_states)
         return key_states, value_states                     # only the new tokens: the rest stays quantized
 
     def get_seq_length(self) -> int:
-        return len(self.store)
+        """Length the NEXT forward will see.  With `evict` set the trim is applied lazily at the next update(), but it is
+        reported here already, so position ids and mask sizes equal those of the reference's loops, which trim right after
+        every step (benchmarker.py:199-205)."""
+        n = len(self.store)
+        if self.evict is None or n == 0:
+            return n
+        if self.paged_block_size is not None:
+            return self.store.length_after_sliding_window(self.evict.get("window_size", 256))
+        return self.store.length_after_evict(**self.evict)
 
     def get_mask_sizes(self, query_length: int) -> Tuple[int, int]:
         return self.get_seq_length() + query_length, 0
@@ -127,24 +157,42 @@ class KvqFusedCache(Cache):
         return tuple(layer.store.get_kv() for layer in self.layers)
 
 
+def _stock_attention(module, query, key, value, attention_mask, dropout, scaling, **kwargs):
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    return ALL_ATTENTION_FUNCTIONS["sdpa"](module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
+
+
 def kvq_fused_attention(module, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                         attention_mask: Optional[torch.Tensor], dropout: float = 0.0, scaling: Optional[float] = None,
                         **kwargs):
     """Attention function registered under "kvq_fused" (transformers AttentionInterface signature).
 
-    query [B,Hq,q_len,D]; key / value are what KvqCacheLayer.update returned: the new tokens only."""
-    layer = _pending.pop(getattr(module, "layer_idx", None), None)
-    q_len = query.size(2)
-    if layer is None or q_len != 1 or layer.cached_before_update == 0 or key.size(2) != 1:
-        # prefill (or a module without our cache): stock attention over the tokens at hand
-        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
-        return ALL_ATTENTION_FUNCTIONS["sdpa"](module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
+    query [B,Hq,q_len,D]; key / value are what KvqCacheLayer.update returned: the new tokens only.
+      * no cached tokens (prefill): stock attention over the tokens at hand, like the reference's first forward;
+      * one query token, every cached token visible: the fused dequant kernel (cached tokens from codes, the step's token exact);
+      * anything the fused kernel does not implement -- a mask that hides cached tokens (left padding), a sliding-window or
+        soft-capped attention module, more than one query token on a non-empty cache -- takes the dequantize path:
+        cached tokens dequantized (QuantizedLayerKV.get_kv), concatenated with the new ones, stock attention with the mask.
+    """
+    ent = _pending().pop(getattr(module, "layer_idx", None), None)
+    if ent is None or ent[1] is not key:
+        return _stock_attention(module, query, key, value, attention_mask, dropout, scaling, **kwargs)  # not our cache
+    layer = ent[0]
     T = layer.cached_before_update
-    if layer.paged_block_size is not None:
-        out = layer.store.attend(query, sm_scale=scaling, k_cur=key, v_cur=value, out_dtype=query.dtype, seq_len=T)
-        return out.transpose(1, 2), None
-    out = layer.store.attend(query, T, key, value, scaling, query.dtype)
-    return out.transpose(1, 2), None  # [B, 1, Hq, D], like the stock attention functions
+    if T == 0:
+        return _stock_attention(module, query, key, value, attention_mask, dropout, scaling, **kwargs)
+    special = (kwargs.get("sliding_window") is not None or kwargs.get("softcap") is not None
+               or getattr(module, "sliding_window", None) is not None or getattr(module, "attn_logit_softcapping", None) is not None)
+    if query.size(2) == 1 and key.size(2) == 1 and not special and _mask_is_trivial(attention_mask):
+        if layer.paged_block_size is not None:
+            out = layer.store.attend(query, sm_scale=scaling, k_cur=key, v_cur=value, out_dtype=query.dtype, seq_len=T)
+        else:
+            out = layer.store.attend(query, T, key, value, scaling, query.dtype)
+        return out.transpose(1, 2), None  # [B, 1, Hq, D], like the stock attention functions
+    kd, vd = layer.store.get_kv()
+    k_all = torch.cat([kd[:, :, :T].to(key.dtype), key], dim=2)
+    v_all = torch.cat([vd[:, :, :T].to(value.dtype), value], dim=2)
+    return _stock_attention(module, query, k_all, v_all, attention_mask, dropout, scaling, **kwargs)
 
 
 def register() -> None:
@@ -172,4 +220,4 @@ def fused_attention(model):
         yield
     finally:
         model.config._attn_implementation = old
-        _pending.clear()
+        _pending().clear()

@@ -259,7 +259,15 @@ class _TokenStore:
         # out of room at the tail: move the live tokens to the front of a buffer that is large enough
         # (a window close to the capacity would otherwise re-copy the live store every cap - need steps: grow so that a copy
         # is amortised over at least `need` appends)
-        new_cap = cap if 2 * need <= cap else max(cap, 2 << (need - 1).bit_length())
+        if 2 * need <= cap:
+            # start + need > cap and need <= cap / 2  =>  start > T: the live rows move to the front of the SAME buffers
+            # (source and destination cannot overlap), no allocation
+            self.codes[:, :, : self.T].copy_(self.live_codes())
+            self.scales[: self.T].copy_(self.live_scales())
+            self.scales_f32[: self.T].copy_(self.live_scales_f32())
+            self.start = 0
+            return
+        new_cap = max(cap, 2 << (need - 1).bit_length())
         codes = torch.empty((B, H, new_cap, W), dtype=self.codes.dtype, device=x.device)
         codes[:, :, : self.T].copy_(self.live_codes())
         scales = torch.empty(new_cap, dtype=self.scales.dtype, device=x.device)
@@ -518,6 +526,17 @@ class QuantizedLayerKV:
             self._k.evict(plan, table, kept)
             self._v.evict(plan, table, kept)
         return self._k.T
+
+    def length_after_evict(self, strategy: str, window_size: int = 256, prefix_len: int = 0, stride: int = 4, block_size: int = 64,
+                           keep_per_block: int = 8, old_budget: int = 64) -> int:
+        """len(self) after evict(...) with the same arguments, without touching the store (host arithmetic)."""
+        from ..cache.implementations import evict_plan
+        if strategy not in self._STRATEGIES:
+            raise ValueError(f"unknown eviction strategy {strategy!r}; one of {sorted(self._STRATEGIES)}")
+        if self._k.T == 0:
+            return 0
+        return int(evict_plan(self._STRATEGIES[strategy], self._k.T, window=window_size, prefix=prefix_len, stride=stride,
+                              block=block_size, keep=keep_per_block, budget=old_budget).n_total)
 
     def quantized(self):
         """(k_codes, k_scales_f32, k_bits, v_codes, v_scales_f32, v_bits) views of the live store, for

@@ -198,3 +198,83 @@ def test_fused_attention_on_a_paged_store(bench):
         bench.generate_with_quantized_kv(PROMPT, 2, mode="int8", paged_block_size=16)
     with pytest.raises(ValueError):
         bench.generate_with_quantized_kv(PROMPT, 2, mode="int8", fused_attention=True, paged_block_size=16, evict={"strategy": "strided"})
+
+
+def test_fused_attention_honours_a_padding_mask(bench):
+    """A left-padded batch: the mask hides cached tokens, so the step must not take the fused kernel (which sees every cached
+    token); it takes the dequantize path with the mask and agrees with the reference-style loop."""
+    from kvq_b200.hf_cache import KvqFusedCache, fused_attention
+    from kvq_b200.quantization import QuantizedKVCache
+    from transformers import DynamicCache
+    model = bench.model
+    ids = StubTokenizer(batch=2)(PROMPT[:40]).input_ids.cuda()
+    mask = torch.ones_like(ids)
+    mask[0, :7] = 0  # row 0 is left-padded
+    out = model(input_ids=ids, attention_mask=mask, use_cache=True)
+    kv = tuple((l.keys, l.values) for l in out.past_key_values.layers)
+    qc = QuantizedKVCache(n_layers=len(kv), mode="mixed", device="cuda", compute_dtype=torch.float16)
+    qc.init_from_prompt_past(kv)
+    nxt = torch.argmax(out.logits[:, -1, :], dim=-1, keepdim=True)
+    mask2 = torch.cat([mask, torch.ones_like(nxt)], dim=1)
+    ref = model(input_ids=nxt, attention_mask=mask2, use_cache=True, past_key_values=DynamicCache(ddp_cache_data=qc.to_past_key_values()))
+    cache = KvqFusedCache(len(kv), mode="mixed", compute_dtype=torch.float16)
+    with fused_attention(model):
+        model(input_ids=ids, attention_mask=mask, use_cache=True, past_key_values=cache)
+        got = model(input_ids=nxt, attention_mask=mask2, use_cache=True, past_key_values=cache)
+        # without padding the same call takes the fused kernel and must differ for the padded row only if the mask matters
+        cache2 = KvqFusedCache(len(kv), mode="mixed", compute_dtype=torch.float16)
+        model(input_ids=ids, use_cache=True, past_key_values=cache2)
+        nomask = model(input_ids=nxt, use_cache=True, past_key_values=cache2)
+    torch.testing.assert_close(got.logits.float(), ref.logits.float(), rtol=2e-2, atol=2e-2)
+    assert not torch.allclose(got.logits[0].float(), nomask.logits[0].float(), rtol=2e-2, atol=2e-2)  # the mask was applied
+
+
+def test_two_caches_in_flight_do_not_cross_read(bench):
+    """_pending is keyed per thread and checked against the key tensor: interleaving two caches on one model is safe."""
+    from kvq_b200.hf_cache import KvqFusedCache, fused_attention
+    model = bench.model
+    a_ids, b_ids = StubTokenizer()(PROMPT).input_ids.cuda(), StubTokenizer()(PROMPT[::-1]).input_ids.cuda()
+    n = model.config.n_layer
+    with fused_attention(model):
+        ca, cb = KvqFusedCache(n, mode="int8"), KvqFusedCache(n, mode="int8")
+        oa, ob = model(input_ids=a_ids, use_cache=True, past_key_values=ca), model(input_ids=b_ids, use_cache=True, past_key_values=cb)
+        ta, tb = oa.logits[:, -1:].argmax(-1), ob.logits[:, -1:].argmax(-1)
+        la = model(input_ids=ta, use_cache=True, past_key_values=ca).logits
+        lb = model(input_ids=tb, use_cache=True, past_key_values=cb).logits
+        solo = KvqFusedCache(n, mode="int8")
+        model(input_ids=a_ids, use_cache=True, past_key_values=solo)
+        la_solo = model(input_ids=ta, use_cache=True, past_key_values=solo).logits
+    assert torch.equal(la, la_solo) and not torch.equal(la, lb)
+
+
+def test_composed_window_sees_the_positions_of_trim_after_step(bench):
+    """quant_mixed + sliding window as ONE cache vs composing the reference functions (quantize the store, trim to the window
+    right after every step, benchmarker.py:199-205): the model must see the same cache length -- hence the same position ids
+    -- and produce the same logits (the lazily trimmed store used to report W + 1)."""
+    from kvq_b200.hf_cache import KvqFusedCache, fused_attention
+    from kvq_b200.quantization import QuantizedKVCache
+    from transformers import DynamicCache
+    model, W = bench.model, 32
+    ids = StubTokenizer()(PROMPT).input_ids.cuda()
+    out = model(input_ids=ids, use_cache=True)
+    kv = tuple((l.keys, l.values) for l in out.past_key_values.layers)
+    qc = QuantizedKVCache(n_layers=len(kv), mode="mixed", device="cuda", compute_dtype=torch.float16)
+    qc.init_from_prompt_past(kv)
+    for l in qc.layers:
+        l.evict("sliding_window", window_size=W)
+    nxt = torch.argmax(out.logits[:, -1, :], dim=-1, keepdim=True)
+    toks, ref_logits = [nxt], []
+    for _ in range(3):
+        o = model(input_ids=toks[-1], use_cache=True, past_key_values=DynamicCache(ddp_cache_data=qc.to_past_key_values()))
+        ref_logits.append(o.logits.float())
+        qc.append_from_past(tuple((l.keys, l.values) for l in o.past_key_values.layers))
+        for l in qc.layers:
+            l.evict("sliding_window", window_size=W)
+        toks.append(torch.argmax(o.logits[:, -1, :], dim=-1, keepdim=True))
+    cache = KvqFusedCache(len(kv), mode="mixed", compute_dtype=torch.float16, evict={"strategy": "sliding_window", "window_size": W})
+    with fused_attention(model):
+        model(input_ids=ids, use_cache=True, past_key_values=cache)
+        for i in range(3):
+            assert cache.get_seq_length() == W
+            got = model(input_ids=toks[i], use_cache=True, past_key_values=cache).logits.float()
+            torch.testing.assert_close(got, ref_logits[i], rtol=2e-2, atol=2e-2)
