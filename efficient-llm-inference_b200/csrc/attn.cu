@@ -16,35 +16,17 @@
 //              memory once per split.
 // Partials (m, l, acc[D]) per (b, hq, split) go to the workspace; a second kernel merges the splits.
 #include <cmath>
-#include <cstdlib>
 
-#include "kvq_common.cuh"
+#include "attn_common.cuh"
+
+#ifndef KVQ_ATTN_IMMA_MIN_G
+#define KVQ_ATTN_IMMA_MIN_G 2   // KVQ_ATTN_AUTO: smallest Hq / H that takes the tensor-core variant
+#endif
 
 namespace kvq {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kTile = 128;  // tokens per tile
-
-struct AttnParams {
-    const void* q; int q_dtype;
-    const uint8_t* k; int64_t kB, kH, kT; const float* k_scale;
-    const uint8_t* v; int64_t vB, vH, vT; const float* v_scale;
-    int B, Hq, H, T;
-    float qk_scale_log2;  // sm_scale * log2(e)
-    int tokens_per_split, n_splits;
-    float* ws_acc;  // [B, Hq, n_splits, D]
-    float* ws_ml;   // [B, Hq, n_splits, 2]
-    // paged store (table != nullptr): k / v are block pools [n_phys][B][H][bs][row], k_scale / v_scale are [n_phys][bs];
-    // logical block i of the sequence lives in physical block table[i]
-    const int32_t* table; int bs, bs_shift; int64_t kBlk, vBlk;
-};
-
-// position of logical token t in the per-token scale arrays
-template <bool PAGED> __device__ __forceinline__ int64_t tok_index(const AttnParams& P, int t) {
-    if constexpr (!PAGED) return t;
-    return (int64_t)__ldg(P.table + (t >> P.bs_shift)) * P.bs + (t & (P.bs - 1));
-}
 
 // 4 codes of one 32-bit word -> 4 floats, exact.  INT8: flip the sign bit so the byte is code+128,
 // drop it into the mantissa of 2^23 (PRMT), subtract 2^23+128.
@@ -288,24 +270,6 @@ __global__ void __launch_bounds__(kThreads) decode_attn_split_kernel(AttnParams 
 #endif
 constexpr int kThreads2 = 256;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // one thread: arm the stage's mbarrier and start the bulk copies of a tile (rows tokens from t0) of plane (b, h).  Contiguous
 // store: one copy per tensor.  Paged store: one copy per tensor per block piece, source address through the block table.
 template <int KROW, int VROW, int KTILE, bool PAGED>
@@ -342,524 +306,6 @@ __device__ __forceinline__ void issue_tile(const AttnParams& P, int b, int h, in
         }
     }
     if (t0 + kTile < P.T) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.table + ((t0 + kTile) >> P.bs_shift)));
-}
-
-template <int KBITS, int VBITS, int G, int D> struct TmaCfg {
-    static constexpr int kKRow = D * KBITS / 8, kVRow = D * VBITS / 8;
-    static constexpr int kKTile = kTile * kKRow, kVTile = kTile * kVRow;
-    static constexpr int kStage = kKTile + kVTile;
-    // three CTAs (24 warps) per SM: 3 x (ring + ~1.2 KB of bookkeeping + 1 KB reserved) must fit 227 KB
-    static constexpr int kStagesRaw = (KVQ_ATTN_RING_KB * 1024) / kStage;
-    static constexpr int kStages = kStagesRaw > 4 ? 4 : (kStagesRaw < 2 ? 2 : kStagesRaw);
-    static constexpr int kRed = kThreads2 * 32 * 4;  // final cross-row-group reduction aliases the ring
-    static constexpr int kBuf = kStages * kStage > kRed ? kStages * kStage : kRed;
-    static constexpr int kSmem = kBuf + G * D * 4 + G * kTile * 4 + G * 8 * 4 + G * 4 + kStages * 8 + 16;
-};
-
-template <int BITS, int N> struct SmemCodes {
-    static constexpr int kBytes = N * BITS / 8;
-    static constexpr int kWords = kBytes >= 4 ? kBytes / 4 : 1;
-    uint32_t w[kWords];
-    __device__ __forceinline__ void load(const uint8_t* p) {
-        if constexpr (kBytes == 2) w[0] = *reinterpret_cast<const unsigned short*>(p);
-        else if constexpr (kBytes == 4) w[0] = *reinterpret_cast<const uint32_t*>(p);
-        else if constexpr (kBytes == 8) { const uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
-        else {
-#pragma unroll
-            for (int i = 0; i < kBytes / 16; ++i) {
-                const uint4 t = *reinterpret_cast<const uint4*>(p + 16 * i);
-                w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-            }
-        }
-    }
-    __device__ __forceinline__ void to_float(float f[N]) const {
-        if constexpr (BITS == 8) {
-#pragma unroll
-            for (int i = 0; i < N / 4; ++i) int8x4_to_float(w[i], f + 4 * i);
-        } else if constexpr (N >= 8) {
-#pragma unroll
-            for (int i = 0; i < N / 8; ++i) int4x8_to_float(w[i], f + 8 * i);
-        } else {
-            float t[8];
-            int4x8_to_float(w[0], t);
-#pragma unroll
-            for (int i = 0; i < N; ++i) f[i] = t[i];
-        }
-    }
-};
-
-template <int KBITS, int VBITS, int G, int D>
-__global__ void __launch_bounds__(kThreads2) decode_attn_tma_kernel(AttnParams P) {
-    using C = TmaCfg<KBITS, VBITS, G, D>;
-    constexpr int LPR = D / 16, KROWS = kThreads2 / LPR, KPASS = kTile / KROWS;
-    constexpr int EV = 32 / G, LPRV = D / EV, VROWS = kThreads2 / LPRV, VPASS = (kTile + VROWS - 1) / VROWS;
-    constexpr bool kQRegs = G <= 2;
-    constexpr int kWarps = kThreads2 / 32;
-    static_assert(G == 1 || G == 2 || G == 4 || G == 8, "G");
-
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float* q_s = reinterpret_cast<float*>(smem_raw + C::kBuf);          // [G][D]
-    float* p_s = q_s + G * D;                                           // [G][kTile] raw scores (log2 domain)
-    float* wmax_s = p_s + G * kTile;                                    // [G][8] per-warp tile maxima
-    float* l_s = wmax_s + G * 8;                                        // [G]
-    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(l_s + G) + 7) & ~uintptr_t(7));
-
-    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t_begin = split * P.tokens_per_split;
-    const int t_end = min(P.T, t_begin + P.tokens_per_split);
-    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
-    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
-    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < G * D; i += kThreads2) {
-        const int g = i / D, d = i - g * D;
-        q_s[i] = load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + (int64_t)h * G + g) * D + d) * P.qk_scale_log2;
-    }
-    if (tid < G) l_s[tid] = 0.f;
-    __syncthreads();
-
-    auto issue = [&](int tile_idx) {  // one thread: arm the stage's mbarrier, start the bulk copies
-        const int s = tile_idx % C::kStages;
-        const int t0 = t_begin + tile_idx * kTile;
-        const int rows = min(kTile, t_end - t0);
-        uint8_t* sb = smem_raw + s * C::kStage;
-        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
-        mbar_expect_tx(&full[s], kb + vb);
-        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
-        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
-    };
-    if (tid == 0) {
-        for (int i = 0; i < C::kStages - 1 && i < n_tiles; ++i) issue(i);
-    }
-
-    const int kc = tid % LPR, kr = tid / LPR;
-    const int vc = tid % LPRV, vr = tid / LPRV;
-    float qr[kQRegs ? G : 1][16];
-    if (kQRegs) {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) qr[g][e] = q_s[g * D + kc * 16 + e];
-    }
-    float acc[G][EV], m_run[G], l_loc[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        m_run[g] = -INFINITY; l_loc[g] = 0.f;
-#pragma unroll
-        for (int e = 0; e < EV; ++e) acc[g][e] = 0.f;
-    }
-
-    // per-token scales of the rows this thread touches: plain (L1/L2-resident) loads, fetched one tile ahead
-    float ksn[KPASS], vsn[VPASS];
-    auto fetch_scales = [&](int tile_idx) {
-        const int t0 = t_begin + tile_idx * kTile;
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) { const int t = t0 + ps * KROWS + kr; ksn[ps] = t < t_end ? __ldg(P.k_scale + t) : 0.f; }
-#pragma unroll
-        for (int ps = 0; ps < VPASS; ++ps) { const int t = t0 + ps * VROWS + vr; vsn[ps] = t < t_end ? __ldg(P.v_scale + t) : 0.f; }
-    };
-    fetch_scales(0);
-
-    for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % C::kStages;
-        if (tid == 0 && it + C::kStages - 1 < n_tiles) issue(it + C::kStages - 1);  // refills the stage released last iteration
-        float ksc[KPASS], vsc[VPASS];
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) ksc[ps] = ksn[ps];
-#pragma unroll
-        for (int ps = 0; ps < VPASS; ++ps) vsc[ps] = vsn[ps];
-        if (it + 1 < n_tiles) fetch_scales(it + 1);
-        while (!mbar_try_wait(&full[s], (it / C::kStages) & 1)) {}
-        const uint8_t* sb = smem_raw + s * C::kStage;
-        const int t0 = t_begin + it * kTile;
-        const int rows = min(kTile, t_end - t0);
-        // ---- K phase: scores (log2 domain) into p_s, per-warp maxima into wmax_s
-        float wm[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) wm[g] = -INFINITY;
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) {
-            const int row = ps * KROWS + kr;
-            SmemCodes<KBITS, 16> kv;
-            kv.load(sb + row * C::kKRow + kc * (16 * KBITS / 8));
-            float f[16];
-            kv.to_float(f);
-            const float sc = ksc[ps];
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float d = 0.f;
-                if (kQRegs) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) d = fmaf(qr[g][e], f[e], d);
-                } else {
-                    const float4* qp = reinterpret_cast<const float4*>(&q_s[g * D + kc * 16]);
-#pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        const float4 qq = qp[e4];
-                        d = fmaf(qq.x, f[4 * e4], d); d = fmaf(qq.y, f[4 * e4 + 1], d);
-                        d = fmaf(qq.z, f[4 * e4 + 2], d); d = fmaf(qq.w, f[4 * e4 + 3], d);
-                    }
-                }
-#pragma unroll
-                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                const float sv = row < rows ? d * sc : -INFINITY;
-                if (kc == 0) p_s[g * kTile + row] = sv;
-                wm[g] = fmaxf(wm[g], sv);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-#pragma unroll
-            for (int o = 16; o >= LPR; o >>= 1) wm[g] = fmaxf(wm[g], __shfl_xor_sync(0xffffffffu, wm[g], o));
-            if (lane == 0) wmax_s[g * 8 + warp] = wm[g];
-        }
-        __syncthreads();
-        // ---- V phase: running max, rescale, exp2 on the fly, accumulate
-        float m_new[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            float mt = -INFINITY;
-#pragma unroll
-            for (int w8 = 0; w8 < kWarps; ++w8) mt = fmaxf(mt, wmax_s[g * 8 + w8]);
-            m_new[g] = fmaxf(m_run[g], mt);
-            const float a = m_run[g] == -INFINITY ? 0.f : exp2f(m_run[g] - m_new[g]);
-            m_run[g] = m_new[g];
-            l_loc[g] *= a;
-#pragma unroll
-            for (int e = 0; e < EV; ++e) acc[g][e] *= a;
-        }
-#pragma unroll
-        for (int ps = 0; ps < VPASS; ++ps) {
-            const int row = ps * VROWS + vr;
-            if (VROWS * VPASS > kTile && row >= kTile) break;
-            SmemCodes<VBITS, EV> vv;
-            vv.load(sb + C::kKTile + row * C::kVRow + vc * (EV * VBITS / 8));
-            float f[EV];
-            vv.to_float(f);
-            const float vs = vsc[ps];
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float sv = p_s[g * kTile + row];
-                const float pw = sv == -INFINITY ? 0.f : exp2f(sv - m_new[g]);
-                if (vc == 0) l_loc[g] += pw;
-                const float w = pw * vs;
-#pragma unroll
-                for (int e = 0; e < EV; ++e) acc[g][e] = fmaf(w, f[e], acc[g][e]);
-            }
-        }
-        __syncthreads();  // releases stage s, p_s and wmax_s
-    }
-
-    // ---- reduce the row groups through shared memory (aliases the ring: every issued tile was consumed)
-    float* red_s = reinterpret_cast<float*>(smem_raw);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (vc == 0 && vr < kTile) atomicAdd(&l_s[g], l_loc[g]);
-#pragma unroll
-        for (int e = 0; e < EV; ++e) red_s[(vr * G + g) * D + vc * EV + e] = acc[g][e];
-    }
-    __syncthreads();
-    for (int o = tid; o < G * D; o += kThreads2) {
-        float sum = 0.f;
-#pragma unroll 4
-        for (int r = 0; r < VROWS; ++r) sum += red_s[r * G * D + o];
-        const int g = o / D, d = o - g * D;
-        const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
-        P.ws_acc[(hq * P.n_splits + split) * D + d] = sum;
-    }
-    if (tid == 0) {  // m_run is identical in every thread
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int64_t hq = (int64_t)b * P.Hq + (int64_t)h * G + g;
-            P.ws_ml[(hq * P.n_splits + split) * 2] = m_run[g];
-            P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = l_s[g];
-        }
-    }
-}
-
-// =====================================================================================================
-// Integer-dot variant for G == 1 (MHA-shape decode: the bandwidth-bound case).  The fp32 variants spend
-// ~3 instructions per K element and ~3.4 per V element (PRMT + FADD to convert a code, FFMA to use it) and
-// are issue-bound at ~35 % of HBM.  Codes are already integers, so both contractions run on DP4A:
-//   scores : q is turned into 24-bit fixed point per head (three balanced signed byte planes, |error| <=
-//            2^-23 max|q|, i.e. fp32 precision); a lane's 16 codes cost 12 DP4A instead of 48 PRMT/FADD/FFMA.
-//   output : the weights p_t * v_scale[t] are turned into 24-bit fixed point against max(v_scale) (p <= 1);
-//            four tokens' code words are byte-transposed in registers (8 PRMT) so that one DP4A accumulates
-//            four tokens of one channel; int32 accumulators are flushed to fp32 only when the running max moves.
-// Same TMA ring, same split / merge protocol as the fp32 TMA variant.
-// =====================================================================================================
-
-__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) { return __dp4a((int)a, (int)b, c); }
-__device__ __forceinline__ int dp4a_us(uint32_t a_unsigned, uint32_t b_signed, int c) {
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_unsigned), "r"(b_signed), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp4a_su(uint32_t a_signed, uint32_t b_unsigned, int c) {
-    int d;
-    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed), "r"(b_unsigned), "r"(c));
-    return d;
-}
-// rows a,b,c,d of 4 bytes -> columns: col[j] = (a_j, b_j, c_j, d_j)
-__device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t col[4]) {
-    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);
-    const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);
-    col[0] = __byte_perm(t0, t1, 0x5410); col[1] = __byte_perm(t0, t1, 0x7632);
-    col[2] = __byte_perm(t2, t3, 0x5410); col[3] = __byte_perm(t2, t3, 0x7632);
-}
-
-constexpr float kFixedMax = 8355000.f;  // < 127 * (65536 + 256 + 1): three balanced byte digits cannot overflow
-
-template <int KBITS, int VBITS, int D>
-__global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams P) {
-    using C = TmaCfg<KBITS, VBITS, 1, D>;
-    constexpr int LPR = D / 16, KROWS = kThreads2 / LPR, KPASS = kTile / KROWS;
-    constexpr int WPR = D / 8;                   // V: lanes per row, each owns 8 consecutive channels
-    constexpr int VROWS = kThreads2 / WPR;       // 16 (D=128) / 32 (D=64)
-    constexpr int TPT = kTile / VROWS;           // tokens per thread per tile: 8 / 4
-    constexpr int NG = TPT / 4;                  // groups of four tokens
-    constexpr int VB = 8 * VBITS / 8;            // bytes a lane reads per row: 8 (INT8) / 4 (INT4)
-    constexpr int kWarps = kThreads2 / 32;
-    static_assert(TPT % 4 == 0, "token groups");
-
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float* p_s = reinterpret_cast<float*>(smem_raw + C::kBuf);          // [kTile] scores; q staging during setup
-    float* wmax_s = p_s + kTile;                                        // [8]
-    float* misc_s = wmax_s + 8;                                         // [8]: 0 = max|q|, 1 = max v_scale, 2.. scratch
-    uint8_t* wq_s = reinterpret_cast<uint8_t*>(misc_s + 8);             // [3][kTile] weight digits, thread order
-    int8_t* qd_s = reinterpret_cast<int8_t*>(wq_s + 3 * kTile);         // [3][D] q digits
-    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(qd_s + 3 * D) + 7) & ~uintptr_t(7));
-
-    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t_begin = split * P.tokens_per_split;
-    const int t_end = min(P.T, t_begin + P.tokens_per_split);
-    const int n_tiles = (t_end - t_begin + kTile - 1) / kTile;
-    const uint8_t* kplane = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
-    const uint8_t* vplane = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < C::kStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    auto issue = [&](int tile_idx) {
-        const int s = tile_idx % C::kStages;
-        const int t0 = t_begin + tile_idx * kTile;
-        const int rows = min(kTile, t_end - t0);
-        uint8_t* sb = smem_raw + s * C::kStage;
-        const uint32_t kb = rows * C::kKRow, vb = rows * C::kVRow;
-        mbar_expect_tx(&full[s], kb + vb);
-        bulk_g2s(sb, kplane + (int64_t)t0 * C::kKRow, kb, &full[s]);
-        bulk_g2s(sb + C::kKTile, vplane + (int64_t)t0 * C::kVRow, vb, &full[s]);
-    };
-    __syncthreads();  // barriers initialised before the first bulk copy can complete on them
-    if (tid == 0) {
-        for (int i = 0; i < C::kStages - 1 && i < n_tiles; ++i) issue(i);
-    }
-
-    // ---- setup: q -> 24-bit fixed point (three signed byte planes); max v_scale of the split
-    float qv = 0.f;
-    if (tid < D) qv = load_scale(P.q, P.q_dtype, ((int64_t)b * P.Hq + h) * D + tid) * P.qk_scale_log2;
-    float vmax = 0.f;
-    for (int t = t_begin + tid; t < t_end; t += kThreads2 * 8) {  // 8 independent loads in flight
-        float v8[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v8[u] = t + u * kThreads2 < t_end ? __ldg(P.v_scale + t + u * kThreads2) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) vmax = fmaxf(vmax, v8[u]);
-    }
-    float qa = fabsf(qv);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { qa = fmaxf(qa, __shfl_xor_sync(0xffffffffu, qa, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); }
-    if (lane == 0) { wmax_s[warp] = qa; p_s[warp] = vmax; }
-    __syncthreads();
-    float qmax = 0.f, vsmax = 0.f;
-#pragma unroll
-    for (int w8 = 0; w8 < kWarps; ++w8) { qmax = fmaxf(qmax, wmax_s[w8]); vsmax = fmaxf(vsmax, p_s[w8]); }
-    const float dq = qmax > 0.f ? qmax / kFixedMax : 1.f;   // q = Q * dq
-    const float dw = vsmax > 0.f ? vsmax / kFixedMax : 1.f; // weight = W * dw
-    const float inv_dw = 1.f / dw;
-    if (tid < D) {
-        const int Q = __float2int_rn(qv / dq);
-        const int d0 = ((Q + 128) & 255) - 128, Q1 = (Q - d0) >> 8;
-        const int d1 = ((Q1 + 128) & 255) - 128, d2 = (Q1 - d1) >> 8;
-        qd_s[tid] = (int8_t)d0; qd_s[D + tid] = (int8_t)d1; qd_s[2 * D + tid] = (int8_t)d2;
-    }
-    __syncthreads();
-
-    const int kc = tid % LPR, kr = tid / LPR;
-    const int vc = tid % WPR, vr = tid / WPR;
-    // this lane's 16 channels of q, three planes x four words, in the element order of the K words
-    uint32_t qk[3][4];
-    int kinit[3];
-#pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
-        const uint4 t = *reinterpret_cast<const uint4*>(qd_s + pl * D + kc * 16);
-        if (KBITS == 8) { qk[pl][0] = t.x; qk[pl][1] = t.y; qk[pl][2] = t.z; qk[pl][3] = t.w; kinit[pl] = 0; }
-        else {
-            // INT4 rows: word j holds elements 8j..8j+7, high nibbles = even elements, low = odd
-            qk[pl][0] = __byte_perm(t.x, t.y, 0x6420); qk[pl][1] = __byte_perm(t.x, t.y, 0x7531);
-            qk[pl][2] = __byte_perm(t.z, t.w, 0x6420); qk[pl][3] = __byte_perm(t.z, t.w, 0x7531);
-            // nibbles are used unsigned (code + 8): start the accumulator at -8 * sum(q digits)
-            kinit[pl] = -8 * (dp4a_ss(0x01010101u, t.x, 0) + dp4a_ss(0x01010101u, t.y, 0) + dp4a_ss(0x01010101u, t.z, 0) +
-                              dp4a_ss(0x01010101u, t.w, 0));
-        }
-    }
-
-    float ksn[KPASS], vsn = 0.f;  // scales one tile ahead: K rows of this lane; V scale of token `tid` of the tile
-    auto fetch_scales = [&](int tile_idx) {
-        const int t0 = t_begin + tile_idx * kTile;
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) { const int t = t0 + ps * KROWS + kr; ksn[ps] = t < t_end ? __ldg(P.k_scale + t) : 0.f; }
-        if (tid < kTile) vsn = t0 + tid < t_end ? __ldg(P.v_scale + t0 + tid) : 0.f;
-    };
-    fetch_scales(0);
-
-    int iacc[8][3];
-    float facc[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) { facc[d] = 0.f; iacc[d][0] = iacc[d][1] = iacc[d][2] = 0; }
-    float m_run = -INFINITY, l_loc = 0.f;
-
-    for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % C::kStages;
-        if (tid == 0 && it + C::kStages - 1 < n_tiles) issue(it + C::kStages - 1);
-        float ksc[KPASS];
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) ksc[ps] = ksn[ps];
-        const float vs_tok = vsn;
-        if (it + 1 < n_tiles) fetch_scales(it + 1);
-        while (!mbar_try_wait(&full[s], (it / C::kStages) & 1)) {}
-        const uint8_t* sb = smem_raw + s * C::kStage;
-        const int rows = min(kTile, t_end - (t_begin + it * kTile));
-
-        // ---- K phase
-        float wm = -INFINITY;
-#pragma unroll
-        for (int ps = 0; ps < KPASS; ++ps) {
-            const int row = ps * KROWS + kr;
-            int a0 = kinit[0], a1 = kinit[1], a2 = kinit[2];
-            if (KBITS == 8) {
-                const uint4 kw = *reinterpret_cast<const uint4*>(sb + row * C::kKRow + kc * 16);
-                const uint32_t w[4] = {kw.x, kw.y, kw.z, kw.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { a0 = dp4a_ss(w[j], qk[0][j], a0); a1 = dp4a_ss(w[j], qk[1][j], a1); a2 = dp4a_ss(w[j], qk[2][j], a2); }
-            } else {
-                const uint2 kw = *reinterpret_cast<const uint2*>(sb + row * C::kKRow + kc * 8);
-                const uint32_t w[4] = {(kw.x >> 4) & 0x0f0f0f0fu, kw.x & 0x0f0f0f0fu, (kw.y >> 4) & 0x0f0f0f0fu, kw.y & 0x0f0f0f0fu};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { a0 = dp4a_us(w[j], qk[0][j], a0); a1 = dp4a_us(w[j], qk[1][j], a1); a2 = dp4a_us(w[j], qk[2][j], a2); }
-            }
-            float d = fmaf((float)a2, 65536.f, fmaf((float)a1, 256.f, (float)a0));
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            const float sv = row < rows ? d * (dq * ksc[ps]) : -INFINITY;
-            if (kc == 0) p_s[row] = sv;
-            wm = fmaxf(wm, sv);
-        }
-#pragma unroll
-        for (int o = 16; o >= LPR; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        if (lane == 0) wmax_s[warp] = wm;
-        __syncthreads();
-
-        // ---- weights: running max, p = exp2(s - m), fixed-point weight digits in thread order
-        float mt = -INFINITY;
-#pragma unroll
-        for (int w8 = 0; w8 < kWarps; ++w8) mt = fmaxf(mt, wmax_s[w8]);
-        const float m_new = fmaxf(m_run, mt);
-        if (m_new != m_run) {  // uniform: flush the integer accumulators into fp32 and rescale
-            const float a = m_run == -INFINITY ? 0.f : exp2f(m_run - m_new);
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const float v = fmaf((float)iacc[d][2], 65536.f, fmaf((float)iacc[d][1], 256.f, (float)iacc[d][0]));
-                facc[d] = fmaf(v, dw, facc[d]) * a;
-                iacc[d][0] = iacc[d][1] = iacc[d][2] = 0;
-            }
-            l_loc *= a;
-            m_run = m_new;
-        }
-        if (tid < kTile) {
-            const float sv = p_s[tid];
-            const float pw = sv == -INFINITY ? 0.f : exp2f(sv - m_new);
-            l_loc += pw;
-            const uint32_t W = (uint32_t)__float2int_rn(pw * vs_tok * inv_dw);
-            const int slot = (tid % VROWS) * TPT + tid / VROWS;  // the TPT tokens of row group vr are contiguous
-            wq_s[slot] = (uint8_t)(W & 255u); wq_s[kTile + slot] = (uint8_t)((W >> 8) & 255u); wq_s[2 * kTile + slot] = (uint8_t)(W >> 16);
-        }
-        __syncthreads();
-
-        // ---- V phase: byte-transpose four tokens' words, one DP4A per (channel, weight plane)
-        uint32_t wd[3][NG];
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
-#pragma unroll
-            for (int j = 0; j < NG; ++j) wd[pl][j] = *reinterpret_cast<const uint32_t*>(wq_s + pl * kTile + vr * TPT + 4 * j);
-#pragma unroll
-        for (int j = 0; j < NG; ++j) {
-            uint32_t lo[4], hi[4];  // INT8: lo = channels 0..3, hi = channels 4..7 (signed bytes); INT4: odd / even channels
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint8_t* src = sb + C::kKTile + (vr + VROWS * (4 * j + i)) * C::kVRow + vc * VB;
-                if (VBITS == 8) { const uint2 t = *reinterpret_cast<const uint2*>(src); lo[i] = t.x; hi[i] = t.y; }
-                else {
-                    const uint32_t t = *reinterpret_cast<const uint32_t*>(src);
-                    lo[i] = __vsub4(t & 0x0f0f0f0fu, 0x08080808u);          // elements 1,3,5,7
-                    hi[i] = __vsub4((t >> 4) & 0x0f0f0f0fu, 0x08080808u);   // elements 0,2,4,6
-                }
-            }
-            uint32_t cl[4], ch[4];
-            transpose4x4(lo[0], lo[1], lo[2], lo[3], cl);
-            transpose4x4(hi[0], hi[1], hi[2], hi[3], ch);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                // channel index inside the lane's 8: INT8 -> lo: c4, hi: 4 + c4; INT4 -> lo: 2*c4 + 1, hi: 2*c4
-                const int dl = VBITS == 8 ? c4 : 2 * c4 + 1, dh = VBITS == 8 ? 4 + c4 : 2 * c4;
-#pragma unroll
-                for (int pl = 0; pl < 3; ++pl) {
-                    iacc[dl][pl] = dp4a_su(cl[c4], wd[pl][j], iacc[dl][pl]);
-                    iacc[dh][pl] = dp4a_su(ch[c4], wd[pl][j], iacc[dh][pl]);
-                }
-            }
-        }
-        __syncthreads();  // releases stage s, p_s, wq_s, wmax_s
-    }
-
-    // ---- final flush, reduce the VROWS row groups and the per-thread sums
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-        const float v = fmaf((float)iacc[d][2], 65536.f, fmaf((float)iacc[d][1], 256.f, (float)iacc[d][0]));
-        facc[d] = fmaf(v, dw, facc[d]);
-    }
-    float* red_s = reinterpret_cast<float*>(smem_raw);  // [VROWS][D], then [kThreads2] for l
-#pragma unroll
-    for (int d = 0; d < 8; ++d) red_s[vr * D + vc * 8 + d] = facc[d];
-    float* lred = red_s + VROWS * D;
-    lred[tid] = tid < kTile ? l_loc : 0.f;
-    __syncthreads();
-    const int64_t hq = (int64_t)b * P.Hq + h;
-    if (tid < D) {
-        float sum = 0.f;
-#pragma unroll 4
-        for (int r = 0; r < VROWS; ++r) sum += red_s[r * D + tid];
-        P.ws_acc[(hq * P.n_splits + split) * D + tid] = sum;
-    }
-    if (warp == kWarps - 1) {
-        float ls = 0.f;
-        for (int i = lane; i < kTile; i += 32) ls += lred[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-        if (lane == 0) {
-            P.ws_ml[(hq * P.n_splits + split) * 2] = m_run;
-            P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = ls;
-        }
-    }
 }
 
 // =====================================================================================================
@@ -900,10 +346,6 @@ __global__ void __launch_bounds__(kThreads2) decode_attn_dp4a_kernel(AttnParams 
 #endif
 
 constexpr float kLazyLog2 = 8.f;  // see the softmax step of decode_attn_gqa_kernel
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // packed fp32 pairs: Blackwell's FFMA2 / FADD2 / FMUL2 (PTX fma.rn.f32x2 ...) do two IEEE fp32 operations per issue slot;
 // a pair lives in a 64-bit register, and a pair whose halves are the same register becomes SASS's scalar-broadcast operand
@@ -1244,6 +686,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
             }
         }
         __syncwarp();                           // p_w / alpha_w are rewritten by the next tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the stage before its async-proxy (bulk copy) refill
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
     }
 
@@ -1320,11 +763,6 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_GQA_CTAS_PER_SM) decode_at
 #define KVQ_ATTN_MHA_CTAS_PER_SM 2
 #endif
 constexpr float kMhaLazyLog2 = 3.f;
-
-__device__ __forceinline__ int float_order_key(float x) {  // monotone float -> int (an involution on the bit pattern)
-    const int b = __float_as_int(x);
-    return b >= 0 ? b : b ^ 0x7fffffff;
-}
 
 template <int KBITS, int VBITS, int D> struct MhaCfg {
     static constexpr int NT = kThreads2, kWarps = NT / 32, WR = kTile / kWarps;  // 16 tokens per warp per tile
@@ -1549,6 +987,7 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
             }
         }
         __syncwarp();                           // wq_w is rewritten by the next tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the stage before its async-proxy (bulk copy) refill
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
     }
 
@@ -1655,37 +1094,6 @@ int launch_merge(unsigned blocks, unsigned threads, cudaStream_t st, const float
     return KVQ_OK;
 }
 
-template <int KBITS, int VBITS, int G, int D>
-int launch_tma(dim3 grid, cudaStream_t st, const AttnParams& P) {
-    using C = TmaCfg<KBITS, VBITS, G, D>;
-    auto kern = decode_attn_tma_kernel<KBITS, VBITS, G, D>;
-    static thread_local int configured_dev = -1;  // per instantiation, per host thread
-    int dev = 0;
-    KVQ_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-        configured_dev = dev;
-    }
-    kern<<<grid, kThreads2, C::kSmem, st>>>(P);
-    return KVQ_OK;
-}
-
-template <int KBITS, int VBITS, int D>
-int launch_dp4a(dim3 grid, cudaStream_t st, const AttnParams& P) {
-    using C = TmaCfg<KBITS, VBITS, 1, D>;
-    constexpr int kSmem = C::kBuf + (kTile + 16) * 4 + 3 * kTile + 3 * D + C::kStages * 8 + 32;
-    auto kern = decode_attn_dp4a_kernel<KBITS, VBITS, D>;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    KVQ_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        KVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        configured_dev = dev;
-    }
-    kern<<<grid, kThreads2, kSmem, st>>>(P);
-    return KVQ_OK;
-}
-
 template <int KBITS, int VBITS, int D>
 int launch_mha(dim3 grid, cudaStream_t st, const AttnParams& P) {
     using C = MhaCfg<KBITS, VBITS, D>;
@@ -1724,23 +1132,13 @@ int launch_gqa(dim3 grid, cudaStream_t st, const AttnParams& P) {
 }
 
 template <int KBITS, int VBITS, int G>
-int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool tma) {
-    if constexpr (G == 1) {  // MHA-shape decode: integer-dot variant (KVQ_ATTN_FP32=1 keeps the fp32 TMA variant for A/B runs)
-        static const bool fp32_only = getenv("KVQ_ATTN_FP32") != nullptr;
-        static const bool block_wide = getenv("KVQ_ATTN_DP4A_BLOCK") != nullptr;  // the first DP4A kernel (block-wide softmax), for A/B runs
-        const bool paged = P.table != nullptr;  // only the per-warp kernels read through a block table
-        if (tma && !fp32_only && block_wide && !paged) return D == 128 ? launch_dp4a<KBITS, VBITS, 128>(grid, st, P) : launch_dp4a<KBITS, VBITS, 64>(grid, st, P);
-        if (tma && (!fp32_only || paged)) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
-    }
-    if constexpr (G == 2) {  // KVQ_ATTN_G2_BLOCK=1: the block-wide fp32 TMA kernel of the first versions, for A/B runs
-        static const bool g2_block = getenv("KVQ_ATTN_G2_BLOCK") != nullptr;
-        if (tma && (!g2_block || P.table != nullptr)) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
-    }
-    if constexpr (G <= 2) {
-        if (tma) return D == 128 ? launch_tma<KBITS, VBITS, G, 128>(grid, st, P) : launch_tma<KBITS, VBITS, G, 64>(grid, st, P);
-    } else {  // GQA groups of 4 / 8 are FFMA-bound: register-tiled variant (KVQ_ATTN_GQA_OLD=1 keeps the first version for A/B runs)
-        static const bool old_gqa = getenv("KVQ_ATTN_GQA_OLD") != nullptr;
-        if (tma && (!old_gqa || P.table != nullptr)) return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
+int launch_split(int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool ring) {
+    // `ring`: every plane's code rows are back to back, so tiles can be staged with bulk copies -- always true for the cache
+    // stores of this package.  G == 1: per-warp DP4A kernel; G in {2, 4, 8}: register-tiled FFMA2 kernel.  Strided rows take
+    // the register-staged fallback.
+    if (ring) {
+        if constexpr (G == 1) return D == 128 ? launch_mha<KBITS, VBITS, 128>(grid, st, P) : launch_mha<KBITS, VBITS, 64>(grid, st, P);
+        else return D == 128 ? launch_gqa<KBITS, VBITS, G, 128>(grid, st, P) : launch_gqa<KBITS, VBITS, G, 64>(grid, st, P);
     }
     if (D == 128) decode_attn_split_kernel<KBITS, VBITS, G, 128><<<grid, kThreads, 0, st>>>(P);
     else decode_attn_split_kernel<KBITS, VBITS, G, 64><<<grid, kThreads, 0, st>>>(P);
@@ -1792,7 +1190,7 @@ namespace {
 // common tail of the contiguous and paged entry points: split geometry, kernel choice, merge
 int run_decode_attn(AttnParams& P, int k_bits, int v_bits, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
                     const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits, bool tma,
-                    cudaStream_t st) {
+                    int variant, cudaStream_t st) {
     P.B = (int)B; P.Hq = (int)Hq; P.H = (int)H; P.T = (int)T;
     P.qk_scale_log2 = sm_scale * 1.4426950408889634f;
     int64_t tps = (T + n_splits - 1) / n_splits;
@@ -1805,7 +1203,9 @@ int run_decode_attn(AttnParams& P, int k_bits, int v_bits, int64_t B, int64_t Hq
     const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
     const int G = (int)(Hq / H);
     int rc;
-    if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
+    if (variant == KVQ_ATTN_AUTO) variant = kvq_decode_attn_default_variant((int64_t)G);
+    if (variant == KVQ_ATTN_IMMA) rc = launch_attn_mma(P, k_bits, v_bits, G, (int)D, grid, st);
+    else if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
     else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P, tma);
     else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P, tma);
     else rc = launch_g<4, 8>(G, (int)D, grid, st, P, tma);
@@ -1829,6 +1229,21 @@ extern "C" int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_code
                                   const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
                                   const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
                                   kvq_stream_t stream) {
+    return kvq_decode_attn_variant(q, q_dtype, k_codes, k_bits, k_stride3, k_scale, v_codes, v_bits, v_stride3, v_scale, B, Hq, H, T, D,
+                                   sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, KVQ_ATTN_AUTO, stream);
+}
+
+extern "C" int kvq_decode_attn_default_variant(int64_t q_heads_per_kv_head) {
+    // G >= 2: every code feeds several query heads and the CUDA-core kernels are FMA-bound, not HBM-bound
+    return q_heads_per_kv_head >= KVQ_ATTN_IMMA_MIN_G ? KVQ_ATTN_IMMA : KVQ_ATTN_CUDA_CORE;
+}
+
+extern "C" int kvq_decode_attn_variant(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                                       const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                                       const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                                       const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
+                                       int variant, kvq_stream_t stream) {
+    KVQ_REQUIRE(variant >= KVQ_ATTN_AUTO && variant <= KVQ_ATTN_IMMA, "unknown attention variant %d", variant);
     KVQ_REQUIRE((k_cur == nullptr) == (v_cur == nullptr), "k_cur and v_cur must be given together");
     KVQ_REQUIRE(q && k_codes && v_codes && k_scale && v_scale && out && workspace, "null pointer");
     KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
@@ -1847,12 +1262,10 @@ extern "C" int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_code
     P.q = q; P.q_dtype = q_dtype;
     P.k = (const uint8_t*)k_codes; P.kB = ks.sB; P.kH = ks.sH; P.kT = ks.sT; P.k_scale = k_scale;
     P.v = (const uint8_t*)v_codes; P.vB = vs.sB; P.vH = vs.sH; P.vT = vs.sT; P.v_scale = v_scale;
-    // the bulk-copy pipeline needs each plane's rows back to back (true for the cache store);
-    // KVQ_ATTN_NO_TMA=1 forces the register-staged variant (A/B measurements)
-    static const bool no_tma = getenv("KVQ_ATTN_NO_TMA") != nullptr;
-    const bool tma = !no_tma && ks.sT == kw && vs.sT == vw;  // (scales are read with plain loads: no alignment demand)
+    // the bulk-copy pipeline needs each plane's rows back to back (true for the cache store); scales are read with plain loads
+    const bool tma = ks.sT == kw && vs.sT == vw;
     return run_decode_attn(P, k_bits, v_bits, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, tma,
-                           (cudaStream_t)stream);
+                           variant, (cudaStream_t)stream);
 }
 
 extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
@@ -1861,6 +1274,18 @@ extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_p
                                      int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur,
                                      const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
                                      kvq_stream_t stream) {
+    return kvq_decode_attn_paged_variant(q, q_dtype, k_pool, k_bits, k_pool_stride3, k_scale_pool, v_pool, v_bits, v_pool_stride3,
+                                         v_scale_pool, block_table, block_size, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype,
+                                         workspace, n_splits, KVQ_ATTN_AUTO, stream);
+}
+
+extern "C" int kvq_decode_attn_paged_variant(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
+                                             const float* k_scale_pool, const void* v_pool, int v_bits, const int64_t v_pool_stride3[3],
+                                             const float* v_scale_pool, const int32_t* block_table, int64_t block_size, int64_t B,
+                                             int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur,
+                                             const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits, int variant,
+                                             kvq_stream_t stream) {
+    KVQ_REQUIRE(variant >= KVQ_ATTN_AUTO && variant <= KVQ_ATTN_IMMA, "unknown attention variant %d", variant);
     KVQ_REQUIRE((k_cur == nullptr) == (v_cur == nullptr), "k_cur and v_cur must be given together");
     KVQ_REQUIRE(q && k_pool && v_pool && k_scale_pool && v_scale_pool && block_table && out && workspace, "null pointer");
     KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
@@ -1890,5 +1315,5 @@ extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_p
     while ((1LL << sh) < block_size) ++sh;
     P.bs_shift = sh;
     return run_decode_attn(P, k_bits, v_bits, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, true,
-                           (cudaStream_t)stream);
+                           variant, (cudaStream_t)stream);
 }

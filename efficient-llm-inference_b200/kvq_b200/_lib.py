@@ -22,6 +22,7 @@ F32, F16, BF16 = 0, 1, 2
 PER_TENSOR, PER_TOKEN = 0, 1
 ABSMAX_COVERS_INPUT = 0x100  # OR into granularity / bits when absmax is the phase-1 result of the same data
 SLIDING, PREFIX_WINDOW, STRIDED, BLOCK, BUDGET = 0, 1, 2, 3, 4
+ATTN_VARIANTS = {"auto": 0, "cuda_core": 1, "imma": 2}  # enum kvq_attn_variant
 
 DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -73,6 +74,11 @@ SIGNATURES = {
                            + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     "kvq_decode_attn": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
                         + [c_f, c_vp, c_int, c_vp, c_int, c_vp]),
+    "kvq_decode_attn_default_variant": (c_int, [c_i64]),
+    "kvq_decode_attn_variant": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp] + [c_i64] * 5
+                                + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp]),
+    "kvq_decode_attn_paged_variant": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp] + [c_i64] * 6
+                                      + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp]),
     "kvq_decode_attn_paged": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp] + [c_i64] * 6
                               + [c_f, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
 }
@@ -170,8 +176,17 @@ def stride3(t4: torch.Tensor) -> ctypes.Array:
 
 
 def ptr_table(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
-    """Device int64 array of the data pointers of `tensors` (one small H2D copy): the argument of the *_batched entry points."""
+    """Device int64 array of the data pointers of `tensors` (one small H2D copy): the argument of the *_batched entry points.
+    KEEP THE RETURNED TENSOR ALIVE until the launch that reads it has been enqueued: `ptr_table(x).data_ptr()` alone frees
+    the table at once and the next allocation reuses its memory."""
     return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(tensors[0].device, non_blocking=True)
+
+
+def ptr_tables(*lists: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Several pointer tables of equal length in ONE device tensor [k, n] (one H2D copy); row i is `lists[i]`'s table, at
+    result[i].data_ptr().  Same lifetime rule as ptr_table."""
+    dev = lists[0][0].device
+    return torch.tensor([[t.data_ptr() for t in ts] for ts in lists], dtype=torch.int64).to(dev, non_blocking=True)
 
 
 def same_layout(tensors: Sequence[torch.Tensor]) -> bool:

@@ -43,8 +43,11 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
                                v_codes: torch.Tensor, v_scales: torch.Tensor, v_bits: int,
                                sm_scale: Optional[float] = None, out_dtype: Optional[torch.dtype] = None,
                                workspace: Optional[torch.Tensor] = None, k_cur: Optional[torch.Tensor] = None,
-                               v_cur: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               v_cur: Optional[torch.Tensor] = None, variant: str = "auto") -> torch.Tensor:
     """out[b,hq] = softmax_t(q[b,hq] . K[b,hq//G,t] * sm_scale) @ V[b,hq//G]  with K/V = codes * scale[t].
+
+    variant: "auto" (default: the library's choice per Hq/H), "cuda_core" (split-K GEMV on CUDA cores) or "imma"
+    (tensor-map TMA + INT8 tensor-core MMA); see enum kvq_attn_variant in include/kvq.h.
 
     q [B,Hq,1,D] (fp32/fp16/bf16); k_codes int8 [B,H,T,D] (k_bits 8) or uint8 [B,H,T,D/2] (k_bits 4);
     k_scales fp32 [T]; v likewise.  D in {64,128}; kernels exist for Hq/H in {1,2,4,8}, any other grouping is run in padded
@@ -60,7 +63,7 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
     if H and Hq % H == 0 and Hq // H not in (1, 2, 4, 8):
         return run_grouped(q, H, (1, 2, 4, 8), lambda qs: decode_attention_quantized(
             qs, k_codes, k_scales, k_bits, v_codes, v_scales, v_bits, sm_scale=sm_scale if sm_scale is not None else float(D) ** -0.5,
-            out_dtype=out_dtype, workspace=workspace, k_cur=k_cur, v_cur=v_cur))
+            out_dtype=out_dtype, workspace=workspace, k_cur=k_cur, v_cur=v_cur, variant=variant))
     if k_codes.size(0) != B or v_codes.size(0) != B or v_codes.size(1) != H or v_codes.size(2) != T:
         raise RuntimeError("K / V code tensors do not match q")
     if k_scales.dtype != torch.float32 or v_scales.dtype != torch.float32:
@@ -85,13 +88,13 @@ def decode_attention_quantized(q: torch.Tensor, k_codes: torch.Tensor, k_scales:
         nbytes = L.lib().kvq_decode_attn_workspace_bytes(B, Hq, H, T, D, ctypes.byref(ns))
         if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
             workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=q.device)
-        L.check(L.lib().kvq_decode_attn_ex(qc.data_ptr(), L.dtype_code(q.dtype), k_codes.data_ptr(), int(k_bits),
-                                           L.stride3(k_codes), k_scales.data_ptr(), v_codes.data_ptr(), int(v_bits),
-                                           L.stride3(v_codes), v_scales.data_ptr(), B, Hq, H, T, D, float(sm_scale),
-                                           k_cur.data_ptr() if k_cur is not None else None,
-                                           v_cur.data_ptr() if v_cur is not None else None,
-                                           out.data_ptr(), L.dtype_code(out_dtype), workspace.data_ptr(), ns.value,
-                                           L.stream_ptr(q.device)), "kvq_decode_attn")
+        L.check(L.lib().kvq_decode_attn_variant(qc.data_ptr(), L.dtype_code(q.dtype), k_codes.data_ptr(), int(k_bits),
+                                                L.stride3(k_codes), k_scales.data_ptr(), v_codes.data_ptr(), int(v_bits),
+                                                L.stride3(v_codes), v_scales.data_ptr(), B, Hq, H, T, D, float(sm_scale),
+                                                k_cur.data_ptr() if k_cur is not None else None,
+                                                v_cur.data_ptr() if v_cur is not None else None,
+                                                out.data_ptr(), L.dtype_code(out_dtype), workspace.data_ptr(), ns.value,
+                                                L.ATTN_VARIANTS[variant], L.stream_ptr(q.device)), "kvq_decode_attn")
         L.count_launch(2)
     return out
 
@@ -101,7 +104,7 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
                            v_pool: torch.Tensor, v_scale_pool: torch.Tensor, v_bits: int, block_table: torch.Tensor,
                            seq_len: int, sm_scale: Optional[float] = None, out_dtype: Optional[torch.dtype] = None,
                            workspace: Optional[torch.Tensor] = None, k_cur: Optional[torch.Tensor] = None,
-                           v_cur: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           v_cur: Optional[torch.Tensor] = None, variant: str = "auto") -> torch.Tensor:
     """decode_attention_quantized over a PAGED store: the kernel walks the block table, nothing is stitched.
 
     k_pool int8 [n_phys,B,H,block_size,D] (k_bits 8) or uint8 [..., D/2] (k_bits 4), contiguous; k_scale_pool fp32
@@ -121,7 +124,7 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
         return run_grouped(q, H, (1, 2, 4, 8), lambda qs: decode_attention_paged(
             qs, k_pool, k_scale_pool, k_bits, v_pool, v_scale_pool, v_bits, block_table, seq_len,
             sm_scale=sm_scale if sm_scale is not None else float(D) ** -0.5, out_dtype=out_dtype, workspace=workspace,
-            k_cur=k_cur, v_cur=v_cur))
+            k_cur=k_cur, v_cur=v_cur, variant=variant))
     if k_scale_pool.dtype != torch.float32 or v_scale_pool.dtype != torch.float32:
         raise RuntimeError("attention reads fp32 scales")
     if tuple(k_scale_pool.shape) != (k_pool.size(0), bs) or tuple(v_scale_pool.shape) != (v_pool.size(0), bs):
@@ -146,12 +149,12 @@ def decode_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, k_scale_pool: 
         nbytes = L.lib().kvq_decode_attn_workspace_bytes(B, Hq, H, seq_len, D, ctypes.byref(ns))
         if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
             workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=q.device)
-        L.check(L.lib().kvq_decode_attn_paged(qc.data_ptr(), L.dtype_code(q.dtype), k_pool.data_ptr(), int(k_bits), None,
-                                              k_scale_pool.data_ptr(), v_pool.data_ptr(), int(v_bits), None,
-                                              v_scale_pool.data_ptr(), block_table.data_ptr(), int(bs), B, Hq, H, int(seq_len), D,
-                                              float(sm_scale), k_cur.data_ptr() if k_cur is not None else None,
-                                              v_cur.data_ptr() if v_cur is not None else None, out.data_ptr(),
-                                              L.dtype_code(out_dtype), workspace.data_ptr(), ns.value, L.stream_ptr(q.device)),
-                "kvq_decode_attn_paged")
+        L.check(L.lib().kvq_decode_attn_paged_variant(qc.data_ptr(), L.dtype_code(q.dtype), k_pool.data_ptr(), int(k_bits), None,
+                                                      k_scale_pool.data_ptr(), v_pool.data_ptr(), int(v_bits), None,
+                                                      v_scale_pool.data_ptr(), block_table.data_ptr(), int(bs), B, Hq, H, int(seq_len), D,
+                                                      float(sm_scale), k_cur.data_ptr() if k_cur is not None else None,
+                                                      v_cur.data_ptr() if v_cur is not None else None, out.data_ptr(),
+                                                      L.dtype_code(out_dtype), workspace.data_ptr(), ns.value, L.ATTN_VARIANTS[variant],
+                                                      L.stream_ptr(q.device)), "kvq_decode_attn_paged")
         L.count_launch(2)
     return out

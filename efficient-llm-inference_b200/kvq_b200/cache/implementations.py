@@ -88,7 +88,8 @@ def gather_tokens_batched(xs: List[torch.Tensor], plan: L.EvictPlan, table: Opti
         table = _old_table(plan, x0.device)
     with L.device_guard(x0):
         sh, st = L.shape_stride(x0)
-        L.check(L.lib().kvq_evict_gather_batched(L.ptr_table(xs).data_ptr(), L.ptr_table(outs).data_ptr(), len(xs), x0.element_size(),
+        tabs = L.ptr_tables(xs, outs)  # alive until the launch is enqueued
+        L.check(L.lib().kvq_evict_gather_batched(tabs[0].data_ptr(), tabs[1].data_ptr(), len(xs), x0.element_size(),
                                                  sh, st, ctypes.byref(plan), table.data_ptr() if table is not None else None, None,
                                                  L.stream_ptr(x0.device)), "kvq_evict_gather_batched")
         L.count_launch()
@@ -207,7 +208,8 @@ def chunk_summarize_kv(past_key_values: tuple, chunk_size: int, keep_last: int) 
         if out.numel():
             with L.device_guard(x0):
                 sh, st = L.shape_stride(x0)
-                L.check(L.lib().kvq_chunk_mean_batched(L.ptr_table(flat).data_ptr(), L.ptr_table(outs).data_ptr(), len(flat),
+                tabs = L.ptr_tables(flat, outs)  # alive until the launch is enqueued
+                L.check(L.lib().kvq_chunk_mean_batched(tabs[0].data_ptr(), tabs[1].data_ptr(), len(flat),
                                                        L.dtype_code(x0.dtype), sh, st, int(chunk_size), int(keep_last),
                                                        L.stream_ptr(x0.device)), "kvq_chunk_mean_batched")
                 L.count_launch()

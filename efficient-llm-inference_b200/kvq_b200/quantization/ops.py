@@ -328,11 +328,10 @@ class _TokenStore:
             if st_.bits != bits or st_.start + st_.T != lo or st_.codes.stride() != cs or st_.scales.dtype != x0.dtype:
                 return False
         sh, st4 = L.shape_stride(x0)
+        tabs = L.ptr_tables(xs, [s_.codes for s_ in stores], [s_.scales for s_ in stores], [s_.scales_f32 for s_ in stores])
         L.check(L.lib().kvq_quant_per_token_fused_batched(
-            L.ptr_table(xs).data_ptr(), L.dtype_code(x0.dtype), len(xs), sh, st4, bits, float(eps),
-            L.ptr_table([s_.codes for s_ in stores]).data_ptr(), L.stride3(s0.codes), lo,
-            L.ptr_table([s_.scales for s_ in stores]).data_ptr(), L.ptr_table([s_.scales_f32 for s_ in stores]).data_ptr(),
-            L.stream_ptr(x0.device)), "kvq_quant_per_token_fused_batched")
+            tabs[0].data_ptr(), L.dtype_code(x0.dtype), len(xs), sh, st4, bits, float(eps), tabs[1].data_ptr(), L.stride3(s0.codes),
+            lo, tabs[2].data_ptr(), tabs[3].data_ptr(), L.stream_ptr(x0.device)), "kvq_quant_per_token_fused_batched")
         L.count_launch()
         for st_ in stores:
             st_.T += n

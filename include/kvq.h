@@ -283,6 +283,21 @@ KVQ_API int kvq_decode_attn_ex(const void* q, int q_dtype, const void* k_codes, 
                                const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
                                kvq_stream_t stream);
 
+/* Kernel families of the decode attention.  KVQ_ATTN_CUDA_CORE: the split-K GEMV on CUDA cores as north_star words it
+ * (per-warp DP4A for Hq/H = 1, register-tiled FFMA2 for 2, 4, 8).  KVQ_ATTN_IMMA: the same split / merge protocol with the
+ * two contractions on the INT8 tensor-core MMA, tiles staged by tensor-map TMA (csrc/attn_mma.cu): at Hq/H > 1 the CUDA-core
+ * kernels are FMA-bound, not HBM-bound, so KVQ_ATTN_AUTO picks IMMA there (kvq_decode_attn_default_variant).  Same results
+ * within the stated attention tolerance; both are always available for A/B measurements. */
+enum kvq_attn_variant { KVQ_ATTN_AUTO = 0, KVQ_ATTN_CUDA_CORE = 1, KVQ_ATTN_IMMA = 2 };
+KVQ_API int kvq_decode_attn_default_variant(int64_t q_heads_per_kv_head);
+
+/* kvq_decode_attn_ex with an explicit kernel family. */
+KVQ_API int kvq_decode_attn_variant(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],
+                                    const float* k_scale, const void* v_codes, int v_bits, const int64_t v_stride3[3],
+                                    const float* v_scale, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
+                                    const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits,
+                                    int variant, kvq_stream_t stream);
+
 /* Same, over a PAGED quantized store (the reference's PagedKVCache only simulates paging and re-stitches the
  * blocks with torch.cat before every use, src/cache/implementations.py:83-106): the kernel reads K/V blocks through the
  * block table, no stitch copy.
@@ -298,6 +313,14 @@ KVQ_API int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool
                           const float* v_scale_pool, const int32_t* block_table, int64_t block_size, int64_t B, int64_t Hq,
                           int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur, const void* v_cur, void* out,
                           int out_dtype, void* workspace, int n_splits, kvq_stream_t stream);
+
+/* kvq_decode_attn_paged with an explicit kernel family. */
+KVQ_API int kvq_decode_attn_paged_variant(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],
+                                          const float* k_scale_pool, const void* v_pool, int v_bits, const int64_t v_pool_stride3[3],
+                                          const float* v_scale_pool, const int32_t* block_table, int64_t block_size, int64_t B,
+                                          int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale, const void* k_cur,
+                                          const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits, int variant,
+                                          kvq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,9 +29,11 @@ def test_golden_attention(kvq):
             continue  # the fused kernel supports head_dim 64 / 128 (GPT-2, Llama); the others are oracle-only cases
         kb, vb = (4 if mode == "int4" else 8), (8 if mode == "int8" else 4)
         q = torch.from_numpy(g[f"{case}/q"]).cuda()
-        out = kvq.decode_attention_quantized(q, torch.from_numpy(g[f"{case}/kstore"]).cuda(), torch.from_numpy(g[f"{case}/kscales"]).cuda(), kb,
-                                             torch.from_numpy(g[f"{case}/vstore"]).cuda(), torch.from_numpy(g[f"{case}/vscales"]).cuda(), vb)
-        torch.testing.assert_close(out.cpu(), torch.from_numpy(g[f"{case}/out"]), rtol=1e-4, atol=1e-5)
+        for variant in ("cuda_core", "imma"):
+            out = kvq.decode_attention_quantized(q, torch.from_numpy(g[f"{case}/kstore"]).cuda(), torch.from_numpy(g[f"{case}/kscales"]).cuda(), kb,
+                                                 torch.from_numpy(g[f"{case}/vstore"]).cuda(), torch.from_numpy(g[f"{case}/vscales"]).cuda(), vb,
+                                                 variant=variant)
+            torch.testing.assert_close(out.cpu(), torch.from_numpy(g[f"{case}/out"]), rtol=1e-4, atol=1e-5)
         ran += 1
     assert ran >= 2
 
@@ -42,7 +44,8 @@ def test_golden_attention(kvq):
                                          (2, 8, 2, 700, 64), (3, 16, 4, 257, 128), (1, 32, 4, 40000, 128),
                                          (1, 3, 3, 1, 64), (2, 2, 2, 17, 128), (1, 8, 1, 1, 128), (2, 8, 2, 2, 64), (1, 1, 1, 33000, 128),
                                          (2, 8, 4, 777, 128), (1, 24, 12, 1500, 64), (4, 4, 2, 130, 64), (1, 2, 1, 9000, 128)])
-def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
+@pytest.mark.parametrize("variant", ["cuda_core", "imma"])
+def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D, variant):
     g = torch.Generator().manual_seed(B * 1000 + T)
     k = torch.randn(B, H, T, D, generator=g)
     k.view(-1)[::97] *= 8
@@ -52,10 +55,12 @@ def test_oracle_attention(kvq, oracle, mode, B, Hq, H, T, D):
     layer.append_tokens(k.cuda(), v.cuda())
     kc, ks, kb, vc, vs, vb = layer.quantized()
     want = oracle.decode_attention(q, kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
-    out = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb)
+    if Hq // H not in (1, 2, 4, 8) and variant == "imma":
+        pytest.skip("padded groupings are covered by test_any_group_size")
+    out = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb, variant=variant)
     torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-5)
     for dt in (torch.float16, torch.bfloat16):
-        o16 = kvq.decode_attention_quantized(q.cuda().to(dt), kc, ks, kb, vc, vs, vb)
+        o16 = kvq.decode_attention_quantized(q.cuda().to(dt), kc, ks, kb, vc, vs, vb, variant=variant)
         want16 = oracle.decode_attention(q.to(dt).float(), kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
         assert o16.dtype == dt
         tol = 2e-3 if dt == torch.float16 else 8e-3
@@ -167,11 +172,12 @@ def test_store_attend_is_the_same_kernel_call(kvq, mode):
         kvq.QuantizedLayerKV(mode, "cuda", torch.float16).attend(q)
 
 
-def test_full_size_cross_variant_consistency(kvq):
-    """C5 per-GPU shard length (T = 65 536) on one KV head: no CPU oracle at this size, so the kernel variants check each other.
-    The register-tiled GQA kernel (fp32 FFMA2, 8 query heads on one KV head), the per-warp DP4A kernel (one query head per KV
-    head, codes repeated), the register-staged fp32 fallback (strided rows) and the paged instantiation all evaluate the same
-    softmax(q k^T) v: GQA == paged bit for bit, the others within fp32 accumulation noise."""
+@pytest.mark.parametrize("variant", ["cuda_core", "imma"])
+def test_full_size_against_fp32_and_across_variants(kvq, variant):
+    """C5's real length (T = 65 536) on one KV head.  (1) Parity at this size: fp32 dequantize + softmax on the GPU (the oracle's
+    formula, torch fp32; 4 accumulations of 64k terms -> compared at rtol 2e-4 of the largest output) for G = 8 and for the
+    MHA shape (codes repeated).  (2) The kernel families check each other: GQA, MHA shape, strided rows (register-staged
+    fallback / strided tensor map) within accumulation noise; the paged instantiation bit for bit."""
     g = torch.Generator(device="cuda").manual_seed(5)
     B, G, T, D = 1, 8, 65536, 128
     kc = torch.randint(-127, 128, (B, 1, T, D), device="cuda", dtype=torch.int8, generator=g)
@@ -179,15 +185,22 @@ def test_full_size_cross_variant_consistency(kvq):
     ks = torch.rand(T, device="cuda", generator=g) * 0.004 + 0.002
     vs = torch.rand(T, device="cuda", generator=g) * 0.01 + 0.01
     q = torch.randn(B, G, 1, D, device="cuda", generator=g)
-    gqa = kvq.decode_attention_quantized(q, kc, ks, 8, vc, vs, 4)
-    mha = kvq.decode_attention_quantized(q, kc.expand(B, G, T, D).contiguous(), ks, 8, vc.expand(B, G, T, D // 2).contiguous(), vs, 4)
+    kd = kc[0, 0].double() * ks.double()[:, None]
+    vd = torch.stack([(vc[0, 0] >> 4).double() - 8.0, (vc[0, 0] & 15).double() - 8.0], dim=-1).reshape(T, D) * vs.double()[:, None]
+    p = torch.softmax(q[0, :, 0].double() @ kd.T * D ** -0.5, dim=-1)
+    want = (p @ vd).float()[None, :, None, :]
+    gqa = kvq.decode_attention_quantized(q, kc, ks, 8, vc, vs, 4, variant=variant)
+    torch.testing.assert_close(gqa, want, rtol=2e-4, atol=2e-4 * float(want.abs().max()))
+    mha = kvq.decode_attention_quantized(q, kc.expand(B, G, T, D).contiguous(), ks, 8, vc.expand(B, G, T, D // 2).contiguous(), vs, 4,
+                                         variant=variant)
+    torch.testing.assert_close(mha, want, rtol=2e-4, atol=2e-4 * float(want.abs().max()))
     torch.testing.assert_close(mha, gqa, rtol=2e-4, atol=2e-5)
-    # strided rows (a [B,H,T,2W] buffer viewed at half width) take the register-staged fp32 kernel
+    # strided rows (a [B,H,T,2W] buffer viewed at half width): register-staged fp32 kernel (cuda_core) / strided tensor map (imma)
     kpad = torch.zeros(B, 1, T, 2 * D, device="cuda", dtype=torch.int8)
     kpad[..., :D] = kc
     vpad = torch.zeros(B, 1, T, D, device="cuda", dtype=torch.uint8)
     vpad[..., : D // 2] = vc
-    split = kvq.decode_attention_quantized(q, kpad[..., :D], ks, 8, vpad[..., : D // 2], vs, 4)
+    split = kvq.decode_attention_quantized(q, kpad[..., :D], ks, 8, vpad[..., : D // 2], vs, 4, variant=variant)
     torch.testing.assert_close(split, gqa, rtol=2e-4, atol=2e-5)
     # paged: same tokens in shuffled 128-token blocks
     bs = 128
@@ -203,12 +216,34 @@ def test_full_size_cross_variant_consistency(kvq):
     vs_pool = torch.empty(nb, bs, device="cuda")
     ks_pool[perm] = ks.view(nb, bs)
     vs_pool[perm] = vs.view(nb, bs)
-    paged = kvq.decode_attention_paged(q, k_pool, ks_pool, 8, v_pool, vs_pool, 4, table, T)
+    paged = kvq.decode_attention_paged(q, k_pool, ks_pool, 8, v_pool, vs_pool, 4, table, T, variant=variant)
     assert torch.equal(paged, gqa)
     # weights sum to one: with V == const the output is that constant (exact up to the scale's rounding), for every variant
     vc1 = torch.full_like(vc, 0xBB)  # nibble 11 -> code +3
-    one = kvq.decode_attention_quantized(q, kc, ks, 8, vc1, torch.full_like(vs, 0.5), 4)
+    one = kvq.decode_attention_quantized(q, kc, ks, 8, vc1, torch.full_like(vs, 0.5), 4, variant=variant)
     torch.testing.assert_close(one, torch.full_like(one, 1.5), rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("variant", ["cuda_core", "imma"])
+@pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
+@pytest.mark.parametrize("bs", [16, 64, 128, 256])
+def test_paged_variants_equal_contiguous(kvq, variant, mode, bs):
+    """Each kernel family over a paged store (every block-size class: several boxes per tile, one box, a piece of a large
+    block) is bit-identical to the same family over the contiguous store, also for a length that ends inside a block."""
+    g = torch.Generator().manual_seed(bs)
+    B, H, G, T, D = 2, 2, 4, 1000, 128
+    k, v = torch.randn(B, H, T, D, generator=g), torch.randn(B, H, T, D, generator=g)
+    q = torch.randn(B, H * G, 1, D, generator=g).cuda()
+    layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float32)
+    layer.append_tokens(k.cuda(), v.cuda())
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    paged = kvq.PagedQuantizedLayerKV(mode, block_size=bs, compute_dtype=torch.float32)
+    paged.append_tokens(k.cuda(), v.cuda())
+    pk, pv = paged._k, paged._v
+    for n in (T, 777):
+        want = kvq.decode_attention_quantized(q, kc[:, :, :n], ks[:n], kb, vc[:, :, :n], vs[:n], vb, variant=variant)
+        got = kvq.decode_attention_paged(q, pk.codes, pk.scales_f32, kb, pv.codes, pv.scales_f32, vb, pk.table, n, variant=variant)
+        assert torch.equal(got, want), (variant, mode, bs, n)
 
 
 @pytest.mark.parametrize("G", [3, 5, 6, 7, 12, 16])
@@ -233,3 +268,32 @@ def test_any_group_size(kvq, oracle, G):
     a = kvq.decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb, k_cur=kcur.cuda(), v_cur=vcur.cuda())
     b = layer.attend(q.cuda(), None, kcur.cuda(), vcur.cuda())
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("variant", ["cuda_core", "imma"])
+@pytest.mark.parametrize("G,mode", [(8, "int8"), (8, "mixed"), (1, "int8")])
+def test_back_to_back_calls_on_a_warm_l2(kvq, variant, G, mode):
+    """Regression for a cross-proxy race found on B200: the ring's stages are read through the generic proxy (ldmatrix /
+    ld.shared) and refilled through the async proxy (TMA / bulk copy).  When the tiles come from a warm L2 -- the same cache
+    attended to again and again, as in a decode loop -- the refill could overtake reads that had been issued but not performed
+    (rare wrong V rows: l exact, accumulators off by 1e-2 .. 1e-1, two runs in three at G = 8).  Fixed by
+    fence.proxy.async before the stage is released.  40 identical calls must give bit-identical, correct results."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B, H, T, D = 1, 32, 3000, 128
+    k = torch.randn(B, H, T, D, device="cuda", generator=g)
+    v = torch.randn(B, H, T, D, device="cuda", generator=g)
+    q = torch.randn(B, H * G, 1, D, device="cuda", generator=g)
+    layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float32)
+    layer.append_tokens(k, v)
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    kd, vd = layer.get_kv()
+    p = torch.softmax(torch.einsum("bhgd,bhtd->bhgt", q[:, :, 0].double().view(B, H, G, D), kd.double()) * D ** -0.5, dim=-1)
+    want = torch.einsum("bhgt,bhtd->bhgd", p, vd.double()).reshape(B, H * G, 1, D).float()
+    first = None
+    for _ in range(40):
+        out = kvq.decode_attention_quantized(q, kc, ks, kb, vc, vs, vb, variant=variant)
+        if first is None:
+            first = out
+            torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-5)
+        else:
+            assert torch.equal(out, first)
