@@ -706,12 +706,13 @@ def run_decode(cx: Ctx):
     ws = torch.empty(64 << 20, dtype=torch.float32, device=dev)
     out = {}
     nbytes = Lyr * (B * Hl * T * (D + D // 2) + 8 * T)   # per rank per step
-    variants = [("mha", 1, None), ("gqa8", 8, None)]
-    for name, G, _ in variants:
+    # both kernel families for both shapes: "auto" is what a caller gets (CUDA-core DP4A at G = 1, INT8 tensor-core MMA at G > 1)
+    variants = [("mha", 1, "auto"), ("mha_imma", 1, "imma"), ("gqa8", 8, "auto"), ("gqa8_cuda_core", 8, "cuda_core")]
+    for name, G, variant in variants:
         q = torch.randn(B, Hl * G, 1, D, device=dev, dtype=torch.bfloat16, generator=g)
 
         # parity at the real length (T = 65536): layer 0, batch 0, every head, against fp32 dequantize + softmax on the GPU
-        got = kvq_b200.decode_attention_quantized(q, kcs[0], ksc, 8, vcs[0], vsc, 4, workspace=ws, out_dtype=torch.float32)
+        got = kvq_b200.decode_attention_quantized(q, kcs[0], ksc, 8, vcs[0], vsc, 4, workspace=ws, out_dtype=torch.float32, variant=variant)
         kd = kcs[0][0].float() * ksc[None, :, None]
         vb = vcs[0][0]
         vd = torch.stack([(vb >> 4).float() - 8.0, (vb & 15).float() - 8.0], dim=-1).reshape(Hl, T, D) * vsc[None, :, None]
@@ -724,7 +725,7 @@ def run_decode(cx: Ctx):
 
         def step():
             for l in range(Lyr):
-                kvq_b200.decode_attention_quantized(q, kcs[l], ksc, 8, vcs[l], vsc, 4, workspace=ws)
+                kvq_b200.decode_attention_quantized(q, kcs[l], ksc, 8, vcs[l], vsc, 4, workspace=ws, variant=variant)
 
         step()
         torch.cuda.synchronize()
@@ -744,8 +745,8 @@ def run_decode(cx: Ctx):
         ms = cx.max_over_ranks(e0.elapsed_time(e1) / n)
         cx.launches += 2 * Lyr * (n + 5)
         out[name] = {"tok_s": B / (ms * 1e-3), "ms_per_step": ms, "gbs_whole_job": nbytes * world / (ms * 1e-3) / 1e9,
-                     "q_heads_per_kv_head": G, "parity_max_rel_err_T65536": err,
-                     "roofline": roofline(f"decode attention split kernel, G={G} (+ merge)", nbytes / Lyr, ms / Lyr, n * Lyr,
+                     "q_heads_per_kv_head": G, "variant": variant, "parity_max_rel_err_T65536": err,
+                     "roofline": roofline(f"decode attention split kernel, G={G}, variant {variant} (+ merge)", nbytes / Lyr, ms / Lyr, n * Lyr,
                                           note="per launch pair (split + merge) = one layer; the 80-layer CUDA graph is timed as a whole")}
         del graph
     out["config"] = (f"Llama-3-70B-shape synthetic KV (L={Lyr}, {c['H']} KV heads, D={D}) batch {B} x {T} context, INT8-K / INT4-V "

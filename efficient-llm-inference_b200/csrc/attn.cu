@@ -1156,14 +1156,25 @@ int launch_g(int G, int D, dim3 grid, cudaStream_t st, const AttnParams& P, bool
 }
 
 int choose_splits(int64_t B, int64_t H, int64_t T, int64_t G) {
-    // one wave of 256-thread CTAs at the variant's CTAs per SM
-    const int64_t per_sm = G == 1 ? KVQ_ATTN_MHA_CTAS_PER_SM : KVQ_ATTN_GQA_CTAS_PER_SM;
-    const int64_t target = per_sm * sm_count();
-    int64_t n = (target + B * H - 1) / (B * H);
-    const int64_t max_n = (T + 255) / 256;
-    if (n > max_n) n = max_n;
-    if (n < 1) n = 1;
-    return (int)n;
+    // The grid is B * H * n CTAs on `slots` resident CTAs (2 per SM for every variant).  A grid of 1.08 waves -- what "one split
+    // more than fits" gives, e.g. 64 planes x 5 splits on 296 slots -- runs its last 24 CTAs on an idle machine and costs almost
+    // a whole extra wave (measured: C5 at N = 1).  Pick the split count with the best wave efficiency
+    //     planes * n / (ceil(planes * n / slots) * slots)
+    // among those that keep a split at >= 4 tiles, charging a little for every extra split (setup + merge work).
+    (void)G;
+    const int64_t slots = 2 * (int64_t)sm_count(), planes = B * H;
+    int64_t max_n = (T + 511) / 512;
+    if (max_n > 64) max_n = 64;
+    if (max_n < 1) max_n = 1;
+    int64_t best = 1;
+    double best_score = -1.0;
+    for (int64_t n = 1; n <= max_n; ++n) {
+        const int64_t ctas = planes * n, waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots);
+        const double score = eff - 0.004 * (double)n - (waves > 1 ? 0.01 * (double)(waves - 1) : 0.0);
+        if (score > best_score) { best_score = score; best = n; }
+    }
+    return (int)best;
 }
 
 }  // namespace

@@ -50,7 +50,12 @@ namespace {
 #endif
 constexpr int kMT = 128;            // threads per CTA
 constexpr int kMW = kMT / 32;       // warps
-constexpr float kLazy = 3.f;        // the reference moves only when a tile maximum exceeds it by 2^kLazy
+// The softmax reference of a head moves only when a tile maximum exceeds it by 2^kLazy (a move costs a flush of every
+// accumulator of the warp).  The weights p * v_scale[t] are 32-bit fixed point against 2^kLazy * max(v_scale): FOUR unsigned byte
+// planes -- which fill the MMA's 16-row tiles exactly for G = 4 and 8, so the fourth plane is free -- i.e. 24 bits below a
+// weight of 1 and 8 bits of headroom above it: after the first tile a reference practically never moves.
+constexpr float kLazy = 8.f;
+constexpr float kWMax = 4294967040.f;   // largest weight word: 2^32 - 256 (exact in fp32, so the conversion cannot overflow)
 
 // byte offset inside a 1024-byte-aligned tile whose rows have ROW bytes -> offset after the TMA swizzle of that row size
 // (CUTLASS Swizzle<log2(ROW/16), 4, 3>: address bits [7, 7 + B) are XOR-ed into bits [4, 4 + B))
@@ -69,10 +74,13 @@ template <int VROW> __device__ __forceinline__ int tok_of(int c, int half, int r
 
 template <int KBITS, int VBITS, int G, int D> struct MmaCfg {
     static constexpr int KROW = D * KBITS / 8, VROW = D * VBITS / 8;
-    static constexpr int kKTile = kTile * KROW, kVTile = kTile * VROW, kStage = kKTile + kVTile;
-    static constexpr int NCOL = 3 * G;                 // (plane, head) pairs
-    static constexpr int U = (NCOL + 7) / 8;           // K phase: MMAs per k-step (B columns)
-    static constexpr int MTV = (NCOL + 15) / 16;       // V phase: m-tiles (A rows)
+    static constexpr int kKTile = kTile * KROW, kVTile = kTile * VROW;
+    static constexpr int kScl = 2 * kTile * 4;                          // k_scale[128] ++ v_scale[128] of the tile, fp32
+    static constexpr int kStage = kKTile + kVTile + kScl;               // (a multiple of 1024: swizzle atoms stay aligned)
+    static constexpr int NCOL = 3 * G;                 // K phase: (q plane, head) pairs = B columns
+    static constexpr int U = (NCOL + 7) / 8;           // K phase: MMAs per k-step
+    static constexpr int NROW = 4 * G;                 // V phase: (weight plane, head) pairs = A rows (4 planes fill the m-tiles exactly)
+    static constexpr int MTV = (NROW + 15) / 16;       // V phase: m-tiles
     static constexpr int NKM = D / 32, NT = D / 8;     // K phase k-steps; V phase n-tiles
     static constexpr int HS = G == 1 ? 1 : 2;          // heads whose score a lane ends up with
     static constexpr int VB = VROW / 8;                // V bytes a lane loads per token: 16 / 8 / 4
@@ -87,8 +95,8 @@ template <int KBITS, int VBITS, int G, int D> struct MmaCfg {
     static constexpr int oFa = oKi + 8 * U * 4;
     static constexpr int oMl = oFa + kMW * G * 4;                       // float [kMW][G][2]
     static constexpr int oScr = oMl + kMW * G * 8;                      // float [kMW]
-    static constexpr int oBar = (oScr + kMW * 4 + 7) & ~7;              // full[S], empty[S]
-    static constexpr int kFixed = oBar + 2 * KVQ_ATTN_MMA_MAX_STAGES * 8;
+    static constexpr int oBar = (oScr + kMW * 4 + 7) & ~7;              // full[S] (mbarriers), then done[S] (u32 counters)
+    static constexpr int kFixed = oBar + KVQ_ATTN_MMA_MAX_STAGES * 8 + KVQ_ATTN_MMA_MAX_STAGES * 4 + 8;
     static constexpr int kBudget = 227 * 1024 / KVQ_ATTN_MMA_CTAS_PER_SM - 1024 /*per-CTA reservation*/ - 1024 /*alignment slack*/ - kFixed;
     static constexpr int kStagesRaw = kBudget / kStage;
     static constexpr int S = kStagesRaw > KVQ_ATTN_MMA_MAX_STAGES ? KVQ_ATTN_MMA_MAX_STAGES : (kStagesRaw < 2 ? 2 : kStagesRaw);
@@ -135,8 +143,8 @@ __global__ void __launch_bounds__(kMT, KVQ_ATTN_MMA_CTAS_PER_SM)
 decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap, AttnParams P) {
     using C = MmaCfg<KBITS, VBITS, G, D>;
     constexpr int KROW = C::KROW, VROW = C::VROW, U = C::U, MTV = C::MTV, NKM = C::NKM, NT = C::NT, HS = C::HS, VB = C::VB, VW = C::VW;
-    constexpr int S = C::S, PD = S > 2 ? S - 1 : 1;   // tiles in flight ahead of the math
-    constexpr int NCOL = C::NCOL;
+    constexpr int S = C::S;
+    constexpr int NCOL = C::NCOL, NROW = C::NROW;
 
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms are 1024-byte aligned
@@ -151,7 +159,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
     float* ml_s = reinterpret_cast<float*>(fx + C::oMl);
     float* scr_s = reinterpret_cast<float*>(fx + C::oScr);
     uint64_t* full = reinterpret_cast<uint64_t*>(fx + C::oBar);
-    uint64_t* empty = full + S;
+    unsigned* done = reinterpret_cast<unsigned*>(full + KVQ_ATTN_MMA_MAX_STAGES);   // warps that have left stage s
 
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,25 +170,33 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMW); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); done[s] = 0u; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&kmap) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&vmap) : "memory");
     }
+    // the tile's scales travel with it (two 512-byte bulk copies) when the scale vectors are 16-byte aligned; otherwise,
+    // for a tile that ends at T, and for a paged store the lanes load their scales themselves
+    const bool scl_bulk = !PAGED && ((reinterpret_cast<uintptr_t>(P.k_scale) | reinterpret_cast<uintptr_t>(P.v_scale)) & 15u) == 0;
     auto issue = [&](int tile_idx) {   // one thread
         const int s = tile_idx % S;
         const int t0 = t_begin + tile_idx * kTile;
         uint8_t* sb = ring + s * C::kStage;
         if constexpr (!PAGED) {
-            mbar_expect_tx(&full[s], C::kStage);   // out-of-range rows of the last tile are zero-filled and counted
+            const bool scl = scl_bulk && t0 + kTile <= t_end;
+            mbar_expect_tx(&full[s], C::kKTile + C::kVTile + (scl ? C::kScl : 0));   // out-of-range rows of the last tile are zero-filled and counted
             tma_load_4d(sb, &kmap, 0, t0, h, b, &full[s]);
             tma_load_4d(sb + C::kKTile, &vmap, 0, t0, h, b, &full[s]);
+            if (scl) {
+                bulk_g2s(sb + C::kKTile + C::kVTile, P.k_scale + t0, kTile * 4, &full[s]);
+                bulk_g2s(sb + C::kKTile + C::kVTile + kTile * 4, P.v_scale + t0, kTile * 4, &full[s]);
+            }
         } else {
             const int rows = min(kTile, t_end - t0);
             const int blk0 = t0 >> P.bs_shift;
             if (P.bs >= kTile) {   // the tile is one 128-row piece of a block
                 const int phys = __ldg(P.table + blk0), w = t0 & (P.bs - 1);
-                mbar_expect_tx(&full[s], C::kStage);
+                mbar_expect_tx(&full[s], C::kKTile + C::kVTile);
                 tma_load_5d(sb, &kmap, 0, w, h, b, phys, &full[s]);
                 tma_load_5d(sb + C::kKTile, &vmap, 0, w, h, b, phys, &full[s]);
             } else {               // 128 / bs whole blocks, one box each
@@ -202,7 +218,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
     };
     __syncthreads();   // barriers initialised before the first copy can complete on them
     if (tid == 0) {
-        for (int i = 0; i < PD && i < n_tiles; ++i) issue(i);
+        for (int i = 0; i < S && i < n_tiles; ++i) issue(i);   // the whole ring; later tiles are issued by whoever frees a stage
     }
 
     // ---------------------------------------------------------------- setup: q planes, max v_scale, per-warp state
@@ -269,7 +285,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
     float vsmax = 0.f;
 #pragma unroll
     for (int w8 = 0; w8 < kMW; ++w8) vsmax = fmaxf(vsmax, scr_s[w8]);
-    const float dw = vsmax > 0.f ? vsmax * exp2f(kLazy) / kFixedMax : 1.f;   // weight = W * dw, W < 2^24
+    const float dw = vsmax > 0.f ? vsmax * exp2f(kLazy) / kWMax : 1.f;   // weight = W * dw, W < 2^32
     const float inv_dw = 1.f / dw;
 
     // this lane's K-phase columns: idx = 8u + 2c + j  ->  (plane, head); weight of the column in the fp32 score; C init
@@ -340,15 +356,15 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         }
         __syncwarp();
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-            const float wpl = dw * (pl == 0 ? 1.f : pl == 1 ? 256.f : 65536.f);
+        for (int pl = 0; pl < 4; ++pl) {
+            const float wpl = dw * (pl == 0 ? 1.f : pl == 1 ? 256.f : pl == 2 ? 65536.f : 16777216.f);
 #pragma unroll
             for (int mt = 0; mt < MTV; ++mt)
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh) {
-                    if (16 * mt + 8 * rh >= NCOL) continue;   // rows that do not exist for this G
+                    if (16 * mt + 8 * rh >= NROW) continue;   // rows that do not exist for this G
                     const int row = 16 * mt + 8 * rh + g;
-                    if (row < NCOL && row / G == pl) {
+                    if (row < NROW && row / G == pl) {
                         float* dst = facc_w + (row % G) * D;
 #pragma unroll
                         for (int j = 0; j < NT; ++j)
@@ -375,34 +391,34 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         __syncwarp();
     };
 
-    // scales of the lane's four tokens, fetched one tile ahead
+    // scales of the lane's four tokens when they do not come with the tile: fetched one tile ahead
     float ks_n[4], vs_n[4];
     auto fetch_scales = [&](int tile_idx) {
         const int t0 = t_begin + tile_idx * kTile;
+        const bool need = tile_idx < n_tiles && !(scl_bulk && t0 + kTile <= t_end);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int t = t0 + my_tok[r];
-            const bool ok = tile_idx < n_tiles && t < t_end;
+            const bool ok = need && t < t_end;
             const int64_t ti = ok ? tok_index<PAGED>(P, t) : 0;
             ks_n[r] = ok ? __ldg(P.k_scale + ti) : 0.f;
             vs_n[r] = ok ? __ldg(P.v_scale + ti) : 0.f;
         }
     };
     fetch_scales(0);
+    constexpr bool kQfRegs = U == 1;   // G <= 2: the lane's q fragments (2 words per k-step) live in registers
+    uint32_t qfr[kQfRegs ? NKM : 1][2];
+    if constexpr (kQfRegs) {
+#pragma unroll
+        for (int km = 0; km < NKM; ++km) { qfr[km][0] = qf_s[(km * 2 + 0) * 32 + lane]; qfr[km][1] = qf_s[(km * 2 + 1) * 32 + lane]; }
+    }
     bool started = false;
 
     for (int it = 0; it < n_tiles; ++it) {
         const int s = it % S;
-        if (tid == 0 && it + PD < n_tiles) {
-            const int nt = it + PD;   // goes into the stage tile nt - S used: every warp must have left it
-            if (nt >= S) mbar_wait(&empty[nt % S], ((nt / S) - 1) & 1);
-            issue(nt);
-        }
-        // Lane 0 of warp 0 may sit in the producer branch (waiting for the slowest warp to leave a stage) for a long time.  The
-        // K phase below is ldmatrix / mma .sync.aligned issued from inline asm, which the compiler does not see as convergent:
-        // without this barrier lanes 1-31 can reach them while lane 0 is still away (observed: rare wrong rows in warp 0).
-        __syncwarp();
-        const int rows = min(kTile, t_end - (t_begin + it * kTile));
+        const int t0 = t_begin + it * kTile;
+        const int rows = min(kTile, t_end - t0);
+        const bool scl_here = scl_bulk && rows == kTile;   // this tile's scales are in the stage
         float ks[4], vs[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) { ks[r] = ks_n[r]; vs[r] = vs_n[r]; }
@@ -411,6 +427,11 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         __syncwarp();   // lanes leave the spin loop one by one: reconverge before the .aligned instructions
         const uint32_t kb = smem_u32(ring + s * C::kStage);
         const uint8_t* vbp = ring + s * C::kStage + C::kKTile;
+        if (scl_here) {
+            const float* sclp = reinterpret_cast<const float*>(vbp + C::kVTile);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { ks[r] = sclp[my_tok[r]]; vs[r] = sclp[kTile + my_tok[r]]; }
+        }
 
         // ---------------------------------------------------------------- K phase
         int sacc[2][U][4];
@@ -423,7 +444,10 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
             for (int km = 0; km < NKM; ++km) {
                 uint32_t b0[U], b1[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { b0[u] = qf_s[((u * NKM + km) * 2 + 0) * 32 + lane]; b1[u] = qf_s[((u * NKM + km) * 2 + 1) * 32 + lane]; }
+                for (int u = 0; u < U; ++u) {
+                    if constexpr (kQfRegs) { b0[u] = qfr[km][0]; b1[u] = qfr[km][1]; }
+                    else { b0[u] = qf_s[((u * NKM + km) * 2 + 0) * 32 + lane]; b1[u] = qf_s[((u * NKM + km) * 2 + 1) * 32 + lane]; }
+                }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     uint32_t a0, a1, a2, a3;
@@ -445,8 +469,10 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
                         const uint32_t x = sub ? w2 : w0, y = sub ? w3 : w1;
                         const uint32_t a0 = (x >> 4) & 0x0f0f0f0fu, a1 = (y >> 4) & 0x0f0f0f0fu, a2 = x & 0x0f0f0f0fu, a3 = y & 0x0f0f0f0fu;
 #pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            imma<false, true>(sacc[mt][u], a0, a1, a2, a3, qf_s[((u * NKM + km) * 2 + 0) * 32 + lane], qf_s[((u * NKM + km) * 2 + 1) * 32 + lane]);
+                        for (int u = 0; u < U; ++u) {
+                            if constexpr (kQfRegs) imma<false, true>(sacc[mt][u], a0, a1, a2, a3, qfr[km][0], qfr[km][1]);
+                            else imma<false, true>(sacc[mt][u], a0, a1, a2, a3, qf_s[((u * NKM + km) * 2 + 0) * 32 + lane], qf_s[((u * NKM + km) * 2 + 1) * 32 + lane]);
+                        }
                     }
                 }
             }
@@ -502,7 +528,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
             for (int r = 0; r < 4; ++r) {
                 const float p = exp2f(sc[r][hs] - m_ref[hs]);   // -inf score -> 0
                 l_run[hs] += p;
-                W[r] = (uint32_t)__float2int_rn(p * vs[r] * inv_dw);
+                W[r] = __float2uint_rn(p * vs[r] * inv_dw);
             }
             if (writer) {   // byte plane pl of the four tokens, in k-slot order, at A-fragment position (row (pl, head), group g)
                 const int hd = head0 + hs, slot = (g & 3) * 2 + (g >> 2);
@@ -511,6 +537,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
                 wp_w[(0 * G + hd) * 8 + slot] = __byte_perm(lo01, lo23, 0x5410);
                 wp_w[(1 * G + hd) * 8 + slot] = __byte_perm(lo01, lo23, 0x7632);
                 wp_w[(2 * G + hd) * 8 + slot] = __byte_perm(hi01, hi23, 0x5410);
+                wp_w[(3 * G + hd) * 8 + slot] = __byte_perm(hi01, hi23, 0x7632);
             }
         }
         __syncwarp();
@@ -521,7 +548,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         for (int mt = 0; mt < MTV; ++mt) {
             const uint2 lo = *reinterpret_cast<const uint2*>(wp_w + (16 * mt + g) * 8 + 2 * c);   // (group (c, 0), group (c, 1)) of row g
             af[mt][0] = lo.x; af[mt][2] = lo.y;
-            if (16 * mt + 8 < NCOL) {
+            if (16 * mt + 8 < NROW) {
                 const uint2 hi = *reinterpret_cast<const uint2*>(wp_w + (16 * mt + 8 + g) * 8 + 2 * c);
                 af[mt][1] = hi.x; af[mt][3] = hi.y;
             } else { af[mt][1] = 0u; af[mt][3] = 0u; }
@@ -530,16 +557,21 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
                 srow[mt][1] = dp4a_us(af[mt][3], 0x01010101u, dp4a_us(af[mt][1], 0x01010101u, srow[mt][1]));
             }
         }
+        uint32_t vw[2][4][VW];   // the lane's piece (VB bytes) of its eight tokens, one vector load each
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint8_t* src = vbp + v_off[hf][r];
+                if constexpr (VW == 4) { const uint4 x = *reinterpret_cast<const uint4*>(src); vw[hf][r][0] = x.x; vw[hf][r][1] = x.y; vw[hf][r][2] = x.z; vw[hf][r][3] = x.w; }
+                else if constexpr (VW == 2) { const uint2 x = *reinterpret_cast<const uint2*>(src); vw[hf][r][0] = x.x; vw[hf][r][1] = x.y; }
+                else vw[hf][r][0] = *reinterpret_cast<const uint32_t*>(src);
+            }
 #pragma unroll
         for (int i = 0; i < VW; ++i) {   // word column i of the lane's piece: 4 byte columns = 4 (INT8) / 8 (INT4) n-tiles
             uint32_t t[2][4];
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t w[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const uint32_t*>(vbp + v_off[hf][r] + 4 * i);
-                transpose4x4(w[0], w[1], w[2], w[3], t[hf]);
-            }
+            for (int hf = 0; hf < 2; ++hf) transpose4x4(vw[hf][0][i], vw[hf][1][i], vw[hf][2][i], vw[hf][3][i], t[hf]);
 #pragma unroll
             for (int bcol = 0; bcol < 4; ++bcol) {
                 if constexpr (VBITS == 8) {
@@ -564,7 +596,14 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         // tiles come from a warm L2 (two in three runs at G = 8 before the fence, none in 80 after).
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();                           // the weight patch is rewritten by the next tile
-        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+        if (lane == 0) {                        // the LAST warp to leave stage s refills it at once: the whole ring stays in flight
+            unsigned old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done[s])) : "memory");
+            if (old == kMW - 1) {
+                done[s] = 0u;   // next touched only after the refilled tile has been consumed
+                if (it + S < n_tiles) issue(it + S);
+            }
+        }
     }
 
     // ---------------------------------------------------------------- end of the split: flush, merge the four warps, write the partial
