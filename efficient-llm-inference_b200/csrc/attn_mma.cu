@@ -247,6 +247,18 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
         }
     }
     float vmax = 0.f;
+    if (scl_bulk) {   // 16-byte-aligned, contiguous scales: 128-bit loads (t_begin is a multiple of the tile)
+        const int n4 = (t_end - t_begin) >> 2;
+        const float4* v4p = reinterpret_cast<const float4*>(P.v_scale + t_begin);
+        for (int i = tid; i < n4; i += kMT * 4) {
+            float4 x[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) x[u4] = i + u4 * kMT < n4 ? __ldg(v4p + i + u4 * kMT) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) vmax = fmaxf(vmax, fmaxf(fmaxf(x[u4].x, x[u4].y), fmaxf(x[u4].z, x[u4].w)));
+        }
+        for (int t = t_begin + 4 * n4 + tid; t < t_end; t += kMT) vmax = fmaxf(vmax, __ldg(P.v_scale + t));
+    } else
     for (int t = t_begin + tid; t < t_end; t += kMT * 8) {   // 8 independent loads in flight
         float v8[8];
 #pragma unroll
@@ -395,16 +407,18 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
     float ks_n[4], vs_n[4];
     auto fetch_scales = [&](int tile_idx) {
         const int t0 = t_begin + tile_idx * kTile;
-        const bool need = tile_idx < n_tiles && !(scl_bulk && t0 + kTile <= t_end);
+        if (tile_idx >= n_tiles || (scl_bulk && t0 + kTile <= t_end)) return;   // (block-uniform) nothing to fetch: comes with the tile
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int t = t0 + my_tok[r];
-            const bool ok = need && t < t_end;
+            const bool ok = t < t_end;
             const int64_t ti = ok ? tok_index<PAGED>(P, t) : 0;
             ks_n[r] = ok ? __ldg(P.k_scale + ti) : 0.f;
             vs_n[r] = ok ? __ldg(P.v_scale + ti) : 0.f;
         }
     };
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { ks_n[r] = 0.f; vs_n[r] = 0.f; }
     fetch_scales(0);
     constexpr bool kQfRegs = U == 1;   // G <= 2: the lane's q fragments (2 words per k-step) live in registers
     uint32_t qfr[kQfRegs ? NKM : 1][2];
@@ -484,10 +498,18 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_co
             float part[HS];
 #pragma unroll
             for (int hs = 0; hs < HS; ++hs) part[hs] = 0.f;
+            if constexpr (G == 8) {   // column block u IS plane u: planes 0 and 1 combine exactly in int32 (|sum| < 2^21 each)
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+                for (int j = 0; j < 2; ++j) {
+                    const int lo = sacc[r >> 1][0][2 * (r & 1) + j] + (sacc[r >> 1][1][2 * (r & 1) + j] << 8);
+                    part[j] = fmaf((float)sacc[r >> 1][2][2 * (r & 1) + j], colw[2][j], (float)lo * colw[0][j]);
+                }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) part[G == 1 ? 0 : j] = fmaf((float)sacc[r >> 1][u][2 * (r & 1) + j], colw[u][j], part[G == 1 ? 0 : j]);
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) part[G == 1 ? 0 : j] = fmaf((float)sacc[r >> 1][u][2 * (r & 1) + j], colw[u][j], part[G == 1 ? 0 : j]);
+            }
 #pragma unroll
             for (int hs = 0; hs < HS; ++hs) {
                 if (G <= 2) part[hs] += __shfl_xor_sync(0xffffffffu, part[hs], 1);

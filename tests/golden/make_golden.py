@@ -14,6 +14,8 @@ Fixture files
   chunk.npz      chunk_summarize_kv (implementations.py:295-346)
   paged.npz      PagedKVCache append/get_kv/bytes (implementations.py:10-121)
   attn.npz       fp32 eager attention over the reference's dequantized cache (benchmarker.py:470-477)
+  benchmarker.npz  KVCacheBenchmarker.generate_with_quantized_kv / generate_with_cache on a seeded random-init GPT-2 small
+                 (benchmarker.py:423-491): greedy tokens, n_new and est_mb for int8 / int4 / mixed (SURVEY section 4 KAT)
 """
 
 import os
@@ -253,8 +255,51 @@ def make_attn():
     np.savez_compressed(os.path.join(HERE, "attn.npz"), **out)
 
 
+class StubTokenizer:
+    """The only tokenizer members the benchmarker touches (benchmarker.py:76-78,95,99); decode() returns the ids."""
+
+    eos_token_id = 50256
+
+    def __init__(self, ids):
+        self.ids = ids
+
+    def __call__(self, prompt, return_tensors="pt", truncation=False, max_length=None):
+        return type("Enc", (), {"input_ids": self.ids})()
+
+    def decode(self, ids, skip_special_tokens=True):
+        return " ".join(str(int(i)) for i in ids)
+
+
+def make_benchmarker():
+    """The reference's quantized decode loop itself (unmodified; transformers >= 5 needs the two-method DynamicCache shim of
+    SURVEY 8c) on GPT2LMHeadModel(GPT2Config()) under torch.manual_seed(0), fp32, CPU: 16 prompt ids, 8 new tokens."""
+    from transformers import DynamicCache, GPT2Config, GPT2LMHeadModel
+    if not hasattr(DynamicCache, "from_legacy_cache"):
+        DynamicCache.to_legacy_cache = lambda self: tuple((l.keys, l.values) for l in self.layers)
+        DynamicCache.from_legacy_cache = classmethod(lambda cls, t: cls(ddp_cache_data=t))
+    from src.benchmarking.benchmarker import KVCacheBenchmarker
+    torch.manual_seed(0)
+    model = GPT2LMHeadModel(GPT2Config()).eval()
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 50257, (1, 16), generator=g)
+    bench = KVCacheBenchmarker(model, StubTokenizer(ids), device="cpu")
+    out = {"prompt_ids": ids.numpy(), "new_tokens": np.array(8)}
+    text, n_new = bench.generate_with_cache("x", max_new_tokens=8)
+    out["full/tokens"] = np.array([int(t) for t in text.split()])
+    for mode in ("int8", "int4", "mixed"):
+        text, n_new, est_mb = bench.generate_with_quantized_kv("x", max_new_tokens=8, mode=mode)
+        out[f"{mode}/tokens"] = np.array([int(t) for t in text.split()])
+        out[f"{mode}/n_new"] = np.array(n_new)
+        out[f"{mode}/est_mb"] = np.array(est_mb, dtype=np.float64)
+        print("benchmarker", mode, n_new, repr(est_mb))
+    np.savez_compressed(os.path.join(HERE, "benchmarker.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "benchmarker":
+        make_benchmarker()
+        sys.exit(0)
     make_quant()
     make_pertoken()
     make_evict()
@@ -262,6 +307,7 @@ if __name__ == "__main__":
     make_chunk()
     make_paged()
     make_attn()
+    make_benchmarker()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -278,3 +278,38 @@ def test_composed_window_sees_the_positions_of_trim_after_step(bench):
             assert cache.get_seq_length() == W
             got = model(input_ids=toks[i], use_cache=True, past_key_values=cache).logits.float()
             torch.testing.assert_close(got, ref_logits[i], rtol=2e-2, atol=2e-2)
+
+
+def test_golden_benchmarker_gpt2_small():
+    """BASELINE C1's model: the reference's own generate_with_quantized_kv on a seeded random-init GPT-2 small (fp32, CPU;
+    tests/golden/make_golden.py::make_benchmarker) vs ours on the GPU with the same weights and prompt.  est_mb must be the
+    reference's number exactly (SURVEY section 4 KAT: 0.424072265625 / 0.213134765625 / 0.318603515625 MB -- codes plus
+    fp32 scales of 24 tokens x 12 layers); n_new equal; greedy-token agreement is reported (a random-init model has nearly
+    flat logits, CPU and GPU matmuls round differently, so an argmax can flip: the first new token -- produced by the
+    exact prefill -- and at least half of the int8 continuation must agree)."""
+    from _golden import load
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from kvq_b200.benchmarking import KVCacheBenchmarker
+    g = load("benchmarker.npz")
+    ids = torch.from_numpy(g["prompt_ids"])
+    torch.manual_seed(0)
+    model = GPT2LMHeadModel(GPT2Config()).eval().cuda()   # same seeded init as the fixture, fp32
+
+    class Tok(StubTokenizer):
+        def __call__(self, prompt, return_tensors="pt", truncation=False, max_length=None):
+            return type("Enc", (), {"input_ids": ids})()
+
+    bench = KVCacheBenchmarker(model, Tok(), device="cuda")
+    n = int(g["new_tokens"])
+    for mode, kat in (("int8", 0.424072265625), ("int4", 0.213134765625), ("mixed", 0.318603515625)):
+        for fused in (False, True):
+            text, n_new, est_mb = bench.generate_with_quantized_kv("x", max_new_tokens=n, mode=mode, fused_attention=fused)
+            assert n_new == int(g[f"{mode}/n_new"]) == n
+            assert est_mb == float(g[f"{mode}/est_mb"]) == kat, (mode, fused, est_mb)
+            got, want = [int(t) for t in text.split()], g[f"{mode}/tokens"].tolist()
+            assert got[:16] == want[:16] == ids[0].tolist()
+            agree = sum(a == b for a, b in zip(got[16:], want[16:])) / n
+            print(f"golden benchmarker {mode} fused={fused}: est_mb {est_mb} == KAT, greedy-token agreement {agree:.2f}")
+            assert got[16] == want[16]
+            if mode == "int8" and not fused:
+                assert agree >= 0.5

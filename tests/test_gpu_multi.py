@@ -1,0 +1,79 @@
+"""N > 1 on real GPUs (skipped with fewer than two): NCCL head-sharded quantization must reproduce the 1-GPU codes and
+scales bit for bit -- per tensor (the helpers with group=...), per token (QuantizedLayerKV(group=...)) -- and the
+head-sharded fused attention must equal the unsharded call.  The only collective is the allreduce(MAX) of the absmax
+bit patterns (kvq_b200.distributed; reference scale over all heads: src/quantization/ops.py:27,:48,:330,:342).
+Run with:  gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu"""
+
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, "efficient-llm-inference_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import kvq_b200
+        from kvq_b200.distributed import shard_heads
+        g = torch.Generator().manual_seed(1234)
+        B, H, T, D = 2, 8, 300, 128
+        x = torch.randn(B, H, T, D, generator=g).to(torch.bfloat16)
+        x[1, H - 1, 7, 3] = 11.0                      # the global max lives in the last rank's shard
+        v = torch.randn(B, H, T, D, generator=g).to(torch.bfloat16)
+        q = torch.randn(B, 4 * H, 1, D, generator=g).to(torch.bfloat16)
+        xd, vd = x.cuda(), v.cuda()
+        mine, vmine = shard_heads(xd, rank, world).contiguous(), shard_heads(vd, rank, world).contiguous()
+        ok = {}
+        # per tensor
+        q8, s8 = kvq_b200.quantize_int8_per_tensor(mine, group=True)
+        p4, s4, _ = kvq_b200.quantize_int4_per_tensor_packed(mine, group=True)
+        f8, fs8 = kvq_b200.quantize_int8_per_tensor(xd)
+        f4, fs4, _ = kvq_b200.quantize_int4_per_tensor_packed(xd)
+        ok["int8 codes"] = torch.equal(q8, shard_heads(f8, rank, world)) and torch.equal(s8, fs8)
+        ok["int4 codes"] = torch.equal(p4, shard_heads(f4, rank, world)) and torch.equal(s4, fs4)
+        # per token store + head-sharded attention (no collective: heads are independent)
+        layer = kvq_b200.QuantizedLayerKV("mixed", "cuda", torch.bfloat16, group=True)
+        layer.append_tokens(mine, vmine)
+        full = kvq_b200.QuantizedLayerKV("mixed", "cuda", torch.bfloat16)
+        full.append_tokens(xd, vd)
+        kc, ks, kb, vc, vs, vb = layer.quantized()
+        fk, fks, _, fv, fvs, _ = full.quantized()
+        ok["per-token codes"] = torch.equal(kc, shard_heads(fk, rank, world)) and torch.equal(vc, shard_heads(fv, rank, world))
+        ok["per-token scales"] = torch.equal(ks, fks) and torch.equal(vs, fvs)
+        Hl = H // world
+        qm = q.cuda()[:, rank * 4 * Hl:(rank + 1) * 4 * Hl]
+        for variant in ("cuda_core", "imma"):
+            a = kvq_b200.decode_attention_quantized(qm.contiguous(), kc, ks, kb, vc, vs, vb, variant=variant)
+            b = kvq_b200.decode_attention_quantized(q.cuda(), fk, fks, kb, fv, fvs, vb, variant=variant)[:, rank * 4 * Hl:(rank + 1) * 4 * Hl]
+            ok[f"attention {variant}"] = torch.equal(a, b)
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("world", [2])
+def test_nccl_head_shards_reproduce_the_single_gpu_codes(world):
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        assert len(ret) == world
+        for rank in range(world):
+            assert all(ret[rank].values()), (rank, dict(ret[rank]))

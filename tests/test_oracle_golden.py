@@ -126,3 +126,17 @@ def test_attention(oracle):
                                       torch.from_numpy(g[f"{case}/vstore"]), vb, torch.from_numpy(g[f"{case}/vscales"]))
         # fp32 eager attention in torch vs double-accumulated oracle: stated tolerance 1e-5
         torch.testing.assert_close(out, torch.from_numpy(g[f"{case}/out"]), rtol=1e-5, atol=1e-5)
+
+
+def test_benchmarker_fixture_matches_the_survey_kat():
+    """benchmarker.npz was produced by the unmodified reference loop (make_golden.py::make_benchmarker): its est_mb values are
+    the SURVEY section 4 known answers, and equal the closed form  layers * tokens * (code bytes + scale bytes)."""
+    g = load("benchmarker.npz")
+    kat = {"int8": 0.424072265625, "int4": 0.213134765625, "mixed": 0.318603515625}
+    L_, H, D, T = 12, 12, 64, 16 + int(g["new_tokens"])
+    for mode, want in kat.items():
+        kb, vb = (4 if mode == "int4" else 8), (8 if mode == "int8" else 4)
+        nbytes = L_ * T * (H * D * kb // 8 + H * D * vb // 8 + 2 * 4)   # fp32 scales on the CPU path (ops.py:271-290)
+        assert float(g[f"{mode}/est_mb"]) == want == nbytes / 1024 ** 2
+        assert g[f"{mode}/tokens"].tolist()[:16] == g["prompt_ids"][0].tolist() and len(g[f"{mode}/tokens"]) == T
+    assert g["int8/tokens"].tolist() == g["full/tokens"].tolist()   # SURVEY: the int8 text equals the full-cache text
