@@ -965,7 +965,9 @@ def run_c2(cx: Ctx):
     out = {"model": "GPT-2 small (124M, random init, fp16)", "new_tokens": 64}
 
     def run(bench, method, **kw):
-        bench.benchmark_method(["x"], method=method, max_new_tokens=4, window_size=256, **kw)  # warm
+        # warm-up at FULL length: the first pass over every sequence length pays CUDA's lazy kernel loading (cuBLAS / SDPA pick
+        # kernels per shape), which a 4-token warm-up does not cover
+        bench.benchmark_method(["x"], method=method, max_new_tokens=64, window_size=256, **kw)
         before = cx.L.launch_count
         r = bench.benchmark_method(["x"], method=method, max_new_tokens=64, window_size=256, **kw)
         cx.launches += cx.L.launch_count - before

@@ -145,6 +145,32 @@ __device__ __forceinline__ float load_scale(const void* p, int dtype, int64_t i)
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
 }
 
+// ----------------------------------------------------------------------------- device: packed fp32 pairs
+// Blackwell's FFMA2 / FADD2 / FMUL2 (PTX fma.rn.f32x2 ...): two IEEE fp32 operations (round-to-nearest-even each, bit-identical to
+// the scalar instructions) per issue slot; a pair lives in a 64-bit register.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ----------------------------------------------------------------------------- device: reductions
 
 // max over the block of a uint32 (REDUX per warp, one smem round); result valid in every thread

@@ -66,6 +66,24 @@ template <int DT, int BITS, bool CLAMP = true, bool TRUE_DIV = false> __device__
     return __float_as_uint(__fadd_rn(q, Q<BITS>::magic));
 }
 
+// Two elements at once on the packed-fp32 pipe (16-bit inputs, division-free quotient): the same four IEEE operations per
+// element as code_word -- q0 = x * y; r = fma(q0, -s, x) (== fma(-q0, s, x)); q = fma(r, y, q0); q + magic -- issued as FMUL2 /
+// FFMA2 / FFMA2 / FADD2, i.e. HALF the issue slots of an issue-bound kernel; results are bit-identical.
+template <int BITS, bool CLAMP> __device__ __forceinline__ void code_word2(float x0, float x1, const Scale& sc, uint32_t& c0, uint32_t& c1) {
+    const f32x2 X = pack2(x0, x1), Y = pack2(sc.y, sc.y), NS = pack2(-sc.s, -sc.s);
+    const f32x2 q0 = fmul2(X, Y);
+    const f32x2 r = ffma2(q0, NS, X);
+    f32x2 q = ffma2(r, Y, q0);
+    if (CLAMP) {
+        float a, b;
+        unpack2(q, a, b);
+        q = pack2(fminf(fmaxf(a, Q<BITS>::lo), Q<BITS>::hi), fminf(fmaxf(b, Q<BITS>::lo), Q<BITS>::hi));
+    }
+    float o0, o1;
+    unpack2(fadd2(q, pack2(Q<BITS>::magic, Q<BITS>::magic)), o0, o1);
+    c0 = __float_as_uint(o0); c1 = __float_as_uint(o1);
+}
+
 __device__ __forceinline__ uint32_t pack4_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
@@ -108,17 +126,30 @@ template <int DT, int BITS, bool CLAMP = true, bool TRUE_DIV = false> __device__
     constexpr int kN = InVec<DT>::kN;
     float f[kN];
     InVec<DT>::widen(v, f);
+    constexpr bool kPairs = DT != KVQ_F32 && !TRUE_DIV;   // division-free path: two elements per packed-fp32 instruction
     if constexpr (BITS == 8) {
         uint32_t c[kN];
+        if constexpr (kPairs) {
 #pragma unroll
-        for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8, CLAMP, TRUE_DIV>(f[i], sc);
+            for (int i = 0; i < kN; i += 2) code_word2<8, CLAMP>(f[i], f[i + 1], sc, c[i], c[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kN; ++i) c[i] = code_word<DT, 8, CLAMP, TRUE_DIV>(f[i], sc);
+        }
         if constexpr (kN == 8) st_stream8(out, make_uint2(pack4_bytes(c[0], c[1], c[2], c[3]), pack4_bytes(c[4], c[5], c[6], c[7])));
         else st_stream4(out, pack4_bytes(c[0], c[1], c[2], c[3]));
     } else {
         uint32_t b[kN / 2];
 #pragma unroll
-        for (int i = 0; i < kN / 2; ++i)
-            b[i] = code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i], sc) * 16u + code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i + 1], sc);  // low byte valid
+        for (int i = 0; i < kN / 2; ++i) {
+            if constexpr (kPairs) {
+                uint32_t hi, lo;
+                code_word2<4, CLAMP>(f[2 * i], f[2 * i + 1], sc, hi, lo);
+                b[i] = hi * 16u + lo;  // low byte valid
+            } else {
+                b[i] = code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i], sc) * 16u + code_word<DT, 4, CLAMP, TRUE_DIV>(f[2 * i + 1], sc);  // low byte valid
+            }
+        }
         if constexpr (kN == 8) st_stream4(out, pack4_bytes(b[0], b[1], b[2], b[3]));
         else *reinterpret_cast<unsigned short*>(out) = (unsigned short)(__byte_perm(b[0], b[1], 0x0040) & 0xffffu);
     }
@@ -368,25 +399,14 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
             }
         }
     }
-    // NV > 0: the next token's vectors are requested before this token's reduction and stores, so the load -> max -> store chain
-    // of one token overlaps the next token's HBM latency (two tokens in registers per thread).
-    uint4 v[kNV], vn[kNV];
-    if (NV > 0 && (int64_t)blockIdx.x < g.T) {
-        const char* x0 = x + (int64_t)blockIdx.x * g.xT;
-#pragma unroll
-        for (int k = 0; k < kNV; ++k) v[k] = xoff[k] != kNone ? ld_stream(x0 + xoff[k]) : make_uint4(0, 0, 0, 0);
-    }
     for (int64_t t = blockIdx.x; t < g.T; t += gridDim.x) {
         const char* xt = x + t * g.xT;
         char* qt = q + t * g.qT;
+        uint4 v[kNV];
         uint32_t m = 0;
         if (NV > 0) {
-            const int64_t tn = t + gridDim.x;
-            if (tn < g.T) {
-                const char* xn = x + tn * g.xT;
 #pragma unroll
-                for (int k = 0; k < kNV; ++k) vn[k] = xoff[k] != kNone ? ld_stream(xn + xoff[k]) : make_uint4(0, 0, 0, 0);
-            }
+            for (int k = 0; k < kNV; ++k) v[k] = xoff[k] != kNone ? ld_stream(xt + xoff[k]) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < kNV; ++k) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[k]));
         } else {
@@ -419,10 +439,6 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
                     quant_store<DT, BITS, kFusedClamp>(ld_stream(xt + xo + (int64_t)c * 16), sc, qt + qo + (int64_t)c * kOut);
                 }
             }
-        }
-        if (NV > 0) {
-#pragma unroll
-            for (int k = 0; k < kNV; ++k) v[k] = vn[k];
         }
         __syncthreads();  // `red` is reused by the next token
     }
