@@ -1002,6 +1002,83 @@ __global__ void __launch_bounds__(kThreads2, KVQ_ATTN_MHA_CTAS_PER_SM) decode_at
     }
 }
 
+
+// =====================================================================================================
+// Any head_dim (1 .. 512), any Hq / H, any strides and alignment: the coverage kernel behind the tiled ones (the reference
+// path takes any model: benchmarker.py:473-477 hands the cache to transformers' attention).  Grid (n_splits, Hq, B), four
+// warps; a warp walks the split's tokens four apart, a lane owns channels lane, lane + 32, ...; byte loads, fp32 math, online
+// softmax per warp, warps merged through shared memory.  Not a bandwidth kernel.
+// =====================================================================================================
+template <int KBITS, int VBITS>
+__global__ void __launch_bounds__(128) decode_attn_generic_kernel(AttnParams P, int D, int G) {
+    constexpr int kMaxPerLane = 16;  // D <= 512
+    __shared__ float red_s[4][512];
+    __shared__ float ml_s[4][2];
+    const int split = blockIdx.x, hq_in = blockIdx.y, b = blockIdx.z, h = hq_in / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_begin = split * P.tokens_per_split, t_end = min(P.T, t_begin + P.tokens_per_split);
+    const int64_t hq = (int64_t)b * P.Hq + hq_in;
+    const int npl = (D + 31) / 32;
+    float qv[kMaxPerLane], acc[kMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int d = lane + 32 * i;
+        qv[i] = (i < npl && d < D) ? load_scale(P.q, P.q_dtype, hq * D + d) * P.qk_scale_log2 : 0.f;
+        acc[i] = 0.f;
+    }
+    const uint8_t* kp = P.k + (int64_t)b * P.kB + (int64_t)h * P.kH;
+    const uint8_t* vp = P.v + (int64_t)b * P.vB + (int64_t)h * P.vH;
+    auto code = [](const uint8_t* row, int d, int bits) -> float {
+        if (bits == 8) return (float)reinterpret_cast<const int8_t*>(row)[d];
+        const uint8_t byte = row[d >> 1];
+        return (float)((d & 1) ? (byte & 15) : (byte >> 4)) - 8.f;
+    };
+    float m = -INFINITY, l = 0.f;
+    for (int t = t_begin + warp; t < t_end; t += 4) {
+        const uint8_t* kr = kp + (int64_t)t * P.kT;
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i) {
+            const int d = lane + 32 * i;
+            if (i < npl && d < D) dot = fmaf(qv[i], code(kr, d, KBITS), dot);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float sc = dot * P.k_scale[t];
+        const float mn = fmaxf(m, sc);
+        const float a = m == -INFINITY ? 0.f : exp2f(m - mn), p = exp2f(sc - mn);
+        const float w = p * P.v_scale[t];
+        const uint8_t* vr = vp + (int64_t)t * P.vT;
+        l = l * a + p;
+        m = mn;
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i) {
+            const int d = lane + 32 * i;
+            if (i < npl && d < D) acc[i] = fmaf(w, code(vr, d, VBITS), acc[i] * a);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int d = lane + 32 * i;
+        if (i < npl && d < D) red_s[warp][d] = acc[i];
+    }
+    if (lane == 0) { ml_s[warp][0] = m; ml_s[warp][1] = l; }
+    __syncthreads();
+    float M = -INFINITY;
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, ml_s[w][0]);
+    for (int d = threadIdx.x; d < D; d += 128) {
+        float sum = 0.f;
+        for (int w = 0; w < 4; ++w) sum += ml_s[w][0] == -INFINITY ? 0.f : red_s[w][d] * exp2f(ml_s[w][0] - M);
+        P.ws_acc[(hq * P.n_splits + split) * D + d] = sum;
+    }
+    if (threadIdx.x == 0) {
+        float L = 0.f;
+        for (int w = 0; w < 4; ++w) L += ml_s[w][0] == -INFINITY ? 0.f : ml_s[w][1] * exp2f(ml_s[w][0] - M);
+        P.ws_ml[(hq * P.n_splits + split) * 2] = M;
+        P.ws_ml[(hq * P.n_splits + split) * 2 + 1] = L;
+    }
+}
+
 // Optional exact "current token" (the reference's decode step sees the new token's K/V unquantized:
 // benchmarker.py:473-477 concatenates them inside the model before they are quantized at :486): it is merged here
 // as one more split with m = q.k_cur * scale, l = 1, acc = v_cur.
@@ -1014,25 +1091,27 @@ struct CurToken {
 template <int ODT>
 __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
                                          void* __restrict__ out, CurToken cur) {
-    __shared__ float dot_s[4];
+    __shared__ float dot_s[16];
     const int64_t hq = blockIdx.x;
-    const int d = threadIdx.x;  // blockDim.x == D (64 or 128)
+    const int d = threadIdx.x;  // blockDim.x == D rounded up to a multiple of 32 (D <= 512)
+    const bool live = d < D;
     float s_cur = -INFINITY, v_cur = 0.f;
     if (cur.k) {  // independent of the split kernel: runs before the dependency wait
         const int64_t kv_row = (hq / cur.G);  // (b * Hq + hq_in) / G == b * H + h  because Hq = G * H
-        float p = load_scale(cur.q, cur.dtype, hq * D + d) * load_scale(cur.k, cur.dtype, kv_row * D + d);
+        float p = live ? load_scale(cur.q, cur.dtype, hq * D + d) * load_scale(cur.k, cur.dtype, kv_row * D + d) : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
         if ((d & 31) == 0) dot_s[d >> 5] = p;
         __syncthreads();
         float tot = 0.f;
-        for (int w = 0; w < D / 32; ++w) tot += dot_s[w];
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += dot_s[w];
         s_cur = tot * cur.qk_scale_log2;
-        v_cur = load_scale(cur.v, cur.dtype, kv_row * D + d);
+        v_cur = live ? load_scale(cur.v, cur.dtype, kv_row * D + d) : 0.f;
     }
     // launched with programmatic stream serialization: everything above this line overlaps the split kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const float2* ml = reinterpret_cast<const float2*>(ws_ml) + hq * n_splits;
+    if (!live) return;
     const float* acc = ws_acc + hq * n_splits * D + d;
     float M = s_cur, num = cur.k ? v_cur : 0.f, den = cur.k ? 1.f : 0.f;
     for (int s0 = 0; s0 < n_splits; s0 += 8) {  // 8 splits per round: independent loads, then an online-softmax merge
@@ -1179,7 +1258,7 @@ namespace {
 // common tail of the contiguous and paged entry points: split geometry, kernel choice, merge
 int run_decode_attn(AttnParams& P, int k_bits, int v_bits, int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, float sm_scale,
                     const void* k_cur, const void* v_cur, void* out, int out_dtype, void* workspace, int n_splits, bool tma,
-                    int variant, cudaStream_t st) {
+                    int variant, cudaStream_t st, bool generic = false) {
     P.B = (int)B; P.Hq = (int)Hq; P.H = (int)H; P.T = (int)T;
     P.qk_scale_log2 = sm_scale * 1.4426950408889634f;
     int64_t tps = (T + n_splits - 1) / n_splits;
@@ -1192,16 +1271,25 @@ int run_decode_attn(AttnParams& P, int k_bits, int v_bits, int64_t B, int64_t Hq
     const dim3 grid((unsigned)n_splits, (unsigned)H, (unsigned)B);
     const int G = (int)(Hq / H);
     int rc;
+    if (generic) {   // head_dim other than 64 / 128, a grouping the tiled kernels are not built for, or unaligned rows
+        const dim3 gg((unsigned)n_splits, (unsigned)Hq, (unsigned)B);
+        if (k_bits == 8 && v_bits == 8) decode_attn_generic_kernel<8, 8><<<gg, 128, 0, st>>>(P, (int)D, G);
+        else if (k_bits == 8 && v_bits == 4) decode_attn_generic_kernel<8, 4><<<gg, 128, 0, st>>>(P, (int)D, G);
+        else if (k_bits == 4 && v_bits == 4) decode_attn_generic_kernel<4, 4><<<gg, 128, 0, st>>>(P, (int)D, G);
+        else decode_attn_generic_kernel<4, 8><<<gg, 128, 0, st>>>(P, (int)D, G);
+        rc = KVQ_OK;
+    } else {
     if (variant == KVQ_ATTN_AUTO) variant = kvq_decode_attn_default_variant((int64_t)G);
     if (variant == KVQ_ATTN_IMMA) rc = launch_attn_mma(P, k_bits, v_bits, G, (int)D, grid, st);
     else if (k_bits == 8 && v_bits == 8) rc = launch_g<8, 8>(G, (int)D, grid, st, P, tma);
     else if (k_bits == 8 && v_bits == 4) rc = launch_g<8, 4>(G, (int)D, grid, st, P, tma);
     else if (k_bits == 4 && v_bits == 4) rc = launch_g<4, 4>(G, (int)D, grid, st, P, tma);
     else rc = launch_g<4, 8>(G, (int)D, grid, st, P, tma);
+    }
     if (rc != KVQ_OK) return rc;
     rc = check_launch("decode_attn_split");
     if (rc != KVQ_OK) return rc;
-    const unsigned mt = (unsigned)D;
+    const unsigned mt = (unsigned)((D + 31) / 32 * 32);
     const CurToken cur{P.q, k_cur, v_cur, P.q_dtype, G, P.qk_scale_log2};
     switch (out_dtype) {
         case KVQ_F32: rc = launch_merge<KVQ_F32>((unsigned)(B * Hq), mt, st, P.ws_acc, P.ws_ml, n_splits, (int)D, out, cur); break;
@@ -1237,16 +1325,18 @@ extern "C" int kvq_decode_attn_variant(const void* q, int q_dtype, const void* k
     KVQ_REQUIRE(q && k_codes && v_codes && k_scale && v_scale && out && workspace, "null pointer");
     KVQ_REQUIRE(q_dtype >= 0 && q_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "bad dtype");
     KVQ_REQUIRE((k_bits == 8 || k_bits == 4) && (v_bits == 8 || v_bits == 4), "k_bits / v_bits must be 8 or 4");
-    KVQ_REQUIRE(D == 64 || D == 128, "decode_attn: head_dim must be 64 or 128 (got %lld)", (long long)D);
-    KVQ_REQUIRE(B >= 1 && H >= 1 && Hq >= 1 && T >= 1 && T <= 0x7fffffff && B <= 65535 && H <= 65535, "bad shape");
+    KVQ_REQUIRE(D >= 1 && D <= 512, "decode_attn: head_dim must be in [1, 512] (got %lld)", (long long)D);
+    KVQ_REQUIRE(B >= 1 && H >= 1 && Hq >= 1 && T >= 1 && T <= 0x7fffffff && B <= 65535 && H <= 65535 && Hq <= 65535, "bad shape");
     KVQ_REQUIRE(Hq % H == 0, "Hq must be a multiple of H");
     KVQ_REQUIRE(n_splits >= 1, "n_splits must be >= 1");
-    const int64_t kw = k_bits == 8 ? D : D / 2, vw = v_bits == 8 ? D : D / 2;
+    const int64_t kw = k_bits == 8 ? D : (D + 1) / 2, vw = v_bits == 8 ? D : (D + 1) / 2;
     const Stride3 ks = make_stride3(k_stride3, H, T, kw), vs = make_stride3(v_stride3, H, T, vw);
     auto al = [](const void* p, const Stride3& s, int a) {
         return reinterpret_cast<uintptr_t>(p) % a == 0 && s.sB % a == 0 && s.sH % a == 0 && s.sT % a == 0;
     };
-    KVQ_REQUIRE(al(k_codes, ks, 16) && al(v_codes, vs, 16), "decode_attn: code tensors must be 16-byte aligned with 16-byte-multiple strides");
+    // the tiled kernels: head_dim 64 / 128, 1 / 2 / 4 / 8 query heads per KV head, 16-byte-aligned rows; everything else -> generic kernel
+    const int64_t Gq = Hq / H;
+    const bool generic = !((D == 64 || D == 128) && (Gq == 1 || Gq == 2 || Gq == 4 || Gq == 8) && al(k_codes, ks, 16) && al(v_codes, vs, 16));
     AttnParams P{};
     P.q = q; P.q_dtype = q_dtype;
     P.k = (const uint8_t*)k_codes; P.kB = ks.sB; P.kH = ks.sH; P.kT = ks.sT; P.k_scale = k_scale;
@@ -1254,7 +1344,7 @@ extern "C" int kvq_decode_attn_variant(const void* q, int q_dtype, const void* k
     // the bulk-copy pipeline needs each plane's rows back to back (true for the cache store); scales are read with plain loads
     const bool tma = ks.sT == kw && vs.sT == vw;
     return run_decode_attn(P, k_bits, v_bits, B, Hq, H, T, D, sm_scale, k_cur, v_cur, out, out_dtype, workspace, n_splits, tma,
-                           variant, (cudaStream_t)stream);
+                           variant, (cudaStream_t)stream, generic);
 }
 
 extern "C" int kvq_decode_attn_paged(const void* q, int q_dtype, const void* k_pool, int k_bits, const int64_t k_pool_stride3[3],

@@ -64,8 +64,10 @@ class _PagedStream:
         if n:
             self.table[:n].copy_(torch.tensor(self.table_host, dtype=torch.int32), non_blocking=True)
 
-    def append_per_token(self, x: torch.Tensor, eps: float = 1e-8) -> None:
-        """n tokens, one scale each, quantized straight into their blocks: one launch per block touched."""
+    def append_per_token(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
+        """n tokens, one scale each, quantized straight into their blocks: one launch per block touched.  `group`: the store
+        holds a head shard; the per-token absmax is all-reduced (MAX) over the group between the two phases, so codes and
+        scales equal the unsharded store's, bit for bit."""
         B, H, n, D = x.shape
         if self.codes is not None and (tuple(self.codes.shape[1:3]) != (B, H) or self.D != D or self.scales.dtype != x.dtype):
             raise RuntimeError("appended tensor does not match the cache")
@@ -93,11 +95,21 @@ class _PagedStream:
             src = x if m == n else x[:, :, done: done + m]
             sh, st = L.shape_stride(src)
             slot = phys * self.bs + w
-            L.check(lib.kvq_quant_per_token_fused(src.data_ptr(), dt, sh, st, self.bits, float(eps),
-                                                  codes.data_ptr() + phys * codes.stride(0) + w * codes.stride(3), self._stride3,
-                                                  self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
-                                                  bits.data_ptr(), stream), "kvq_quant_per_token_fused")
-            L.count_launch()
+            dst = codes.data_ptr() + phys * codes.stride(0) + w * codes.stride(3)
+            if group is None:
+                L.check(lib.kvq_quant_per_token_fused(src.data_ptr(), dt, sh, st, self.bits, float(eps), dst, self._stride3,
+                                                      self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
+                                                      bits.data_ptr(), stream), "kvq_quant_per_token_fused")
+                L.count_launch()
+            else:  # head shard: absmax of the shard -> allreduce(MAX) -> quantize with the global per-token scale
+                from ..distributed import allreduce_absmax_
+                gb = torch.empty(m, dtype=torch.int32, device=x.device)
+                L.check(lib.kvq_absmax(src.data_ptr(), dt, sh, st, L.PER_TOKEN, gb.data_ptr(), 0, stream), "kvq_absmax")
+                allreduce_absmax_(gb, group)
+                fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
+                L.check(fn(src.data_ptr(), dt, sh, st, L.PER_TOKEN | L.ABSMAX_COVERS_INPUT, gb.data_ptr(), float(eps), dst, self._stride3,
+                           self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot, stream), "kvq_quant (per token)")
+                L.count_launch(2)
             done += m
         self.T += n
 
@@ -136,8 +148,10 @@ class _PagedStream:
 class PagedQuantizedLayerKV:
     """QuantizedLayerKV (modes "int8", "int4", "mixed") on a paged pool; same per-token codes and scales, bit for bit."""
 
-    def __init__(self, mode: str = "int8", block_size: int = 64, device: str = "cuda", compute_dtype: torch.dtype = torch.float16):
+    def __init__(self, mode: str = "int8", block_size: int = 64, device: str = "cuda", compute_dtype: torch.dtype = torch.float16,
+                 group=None):
         assert mode in ["int8", "int4", "mixed"], f"Invalid mode: {mode}"
+        self.group = group  # torch.distributed group of a head-sharded store (None: single GPU)
         if block_size < 16 or block_size & (block_size - 1):
             raise ValueError("block_size must be a power of two >= 16")
         self.mode, self.block_size, self.device, self.compute_dtype = mode, int(block_size), device, compute_dtype
@@ -169,8 +183,8 @@ class PagedQuantizedLayerKV:
         if k.size(2) == 0:
             return
         with L.device_guard(k):
-            self._k.append_per_token(k)
-            self._v.append_per_token(v)
+            self._k.append_per_token(k, group=self.group)
+            self._v.append_per_token(v, group=self.group)
 
     append = append_tokens
 

@@ -71,8 +71,6 @@ class KvqCacheLayer(CacheLayerMixin):
         self.evict = evict  # e.g. {"strategy": "sliding_window", "window_size": 256}: applied to the store after every step
         self.paged_block_size = paged_block_size
         if paged_block_size is not None:
-            if group is not None:
-                raise ValueError("the paged store is single-GPU (per-token scales of a head shard need the allreduce path)")
             if evict is not None and evict.get("strategy") != "sliding_window":
                 raise ValueError("the paged store evicts by dropping leading blocks: sliding_window only")
         self.store = self._new_store(compute_dtype, group)
@@ -80,7 +78,8 @@ class KvqCacheLayer(CacheLayerMixin):
 
     def _new_store(self, compute_dtype, group):
         if self.paged_block_size is not None:
-            return PagedQuantizedLayerKV(mode=self.mode, block_size=self.paged_block_size, device="cuda", compute_dtype=compute_dtype)
+            return PagedQuantizedLayerKV(mode=self.mode, block_size=self.paged_block_size, device="cuda", compute_dtype=compute_dtype,
+                                         group=group)
         return QuantizedLayerKV(mode=self.mode, device="cuda", compute_dtype=compute_dtype, group=group)
 
     def lazy_initialization(self, key_states: torch.Tensor, value_states: torch.Tensor) -> None:

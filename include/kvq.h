@@ -265,8 +265,9 @@ KVQ_API int kvq_chunk_mean_batched(const void* const* xs, void* const* outs, int
  *   v_codes / v_scale likewise
  *   out      [B, Hq, D]   out_dtype, contiguous
  *   workspace: kvq_decode_attn_workspace_bytes(...) bytes, n_splits as returned there
- * D must be 64 or 128; G = Hq / H must be 1, 2, 4 or 8 (other groupings: call once per chunk of <= 8 query heads per KV
- * head, zero-padding q to the next supported G -- kvq_b200.attention.run_grouped does). */
+ * The tiled kernels take head_dim 64 / 128, Hq / H in {1, 2, 4, 8} and 16-byte-aligned code rows; any other head_dim (1..512),
+ * grouping or alignment runs a generic (correct, not bandwidth-bound) kernel, so the entry accepts every model the reference's
+ * path accepts (benchmarker.py:473-477 hands the cache to transformers' attention).  INT4 rows hold ceil(D / 2) bytes. */
 KVQ_API int64_t kvq_decode_attn_workspace_bytes(int64_t B, int64_t Hq, int64_t H, int64_t T, int64_t D, int* n_splits);
 
 KVQ_API int kvq_decode_attn(const void* q, int q_dtype, const void* k_codes, int k_bits, const int64_t k_stride3[3],

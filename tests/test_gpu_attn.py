@@ -25,8 +25,7 @@ def test_golden_attention(kvq):
     for case in g["cases"]:
         mode = case.split("_")[0]
         D = int(case.split("x")[-1])
-        if D not in (64, 128):
-            continue  # the fused kernel supports head_dim 64 / 128 (GPT-2, Llama); the others are oracle-only cases
+        # head_dim 64 / 128 take the tiled kernels, the other golden cases (16, 8) the generic any-head_dim kernel
         kb, vb = (4 if mode == "int4" else 8), (8 if mode == "int8" else 4)
         q = torch.from_numpy(g[f"{case}/q"]).cuda()
         for variant in ("cuda_core", "imma"):
@@ -35,7 +34,7 @@ def test_golden_attention(kvq):
                                                  variant=variant)
             torch.testing.assert_close(out.cpu(), torch.from_numpy(g[f"{case}/out"]), rtol=1e-4, atol=1e-5)
         ran += 1
-    assert ran >= 2
+    assert ran >= 4
 
 
 @pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
@@ -85,10 +84,10 @@ def test_matches_dequantize_then_attend(kvq):
 
 
 def test_bad_arguments(kvq):
-    q = torch.zeros(1, 2, 1, 32, device="cuda")
-    kc = torch.zeros(1, 2, 4, 32, dtype=torch.int8, device="cuda")
+    q = torch.zeros(1, 2, 1, 600, device="cuda")
+    kc = torch.zeros(1, 2, 4, 600, dtype=torch.int8, device="cuda")
     s = torch.ones(4, device="cuda")
-    with pytest.raises(RuntimeError, match="head_dim"):
+    with pytest.raises(RuntimeError, match="head_dim"):  # 1 .. 512
         kvq.decode_attention_quantized(q, kc, s, 8, kc, s, 8)
     q = torch.zeros(1, 3, 1, 64, device="cuda")
     kc = torch.zeros(1, 2, 4, 64, dtype=torch.int8, device="cuda")
@@ -297,3 +296,29 @@ def test_back_to_back_calls_on_a_warm_l2(kvq, variant, G, mode):
             torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-5)
         else:
             assert torch.equal(out, first)
+
+
+@pytest.mark.parametrize("mode", ["int8", "int4", "mixed"])
+@pytest.mark.parametrize("B,Hq,H,T,D", [(2, 6, 3, 300, 96), (1, 4, 4, 700, 256), (2, 8, 2, 130, 80), (1, 5, 1, 65, 7), (1, 2, 2, 1, 33),
+                                         (1, 24, 2, 200, 64)])
+def test_any_head_dim(kvq, oracle, mode, B, Hq, H, T, D):
+    """Models whose head_dim is not 64 / 128 (96: Phi-3-mini class, 256: Gemma, odd sizes: the reference accepts any model,
+    benchmarker.py:473-477) and groupings beyond 8 run the generic kernel: same tolerance as the tiled ones, with and without
+    the step's own token, through the function, the store and the HF cache path."""
+    g = torch.Generator().manual_seed(D * 7 + T)
+    k, v = torch.randn(B, H, T, D, generator=g), torch.randn(B, H, T, D, generator=g)
+    q = torch.randn(B, Hq, 1, D, generator=g)
+    layer = kvq.QuantizedLayerKV(mode, "cuda", torch.float32)
+    layer.append_tokens(k.cuda(), v.cuda())
+    kc, ks, kb, vc, vs, vb = layer.quantized()
+    want = oracle.decode_attention(q, kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu())
+    import kvq_b200._lib as L
+    from kvq_b200.attention import decode_attention_quantized
+    got = decode_attention_quantized(q.cuda(), kc, ks, kb, vc, vs, vb) if Hq // H <= 8 or D not in (64, 128) else None
+    if got is not None:
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(layer.attend(q.cuda()).cpu(), want, rtol=1e-4, atol=1e-5)
+    o16 = layer.attend(q.cuda().half())
+    assert o16.dtype == torch.float16
+    torch.testing.assert_close(o16.cpu().float(), oracle.decode_attention(q.half().float(), kc.cpu(), kb, ks.cpu(), vc.cpu(), vb, vs.cpu()),
+                               rtol=2e-3, atol=2e-3)
