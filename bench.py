@@ -350,8 +350,7 @@ def workload_config(cfg, n_gpus, where):
                      f"D={cfg['D']}, bf16): INT4 pack/unpack, per-tensor scale, head-sharded over {n_gpus} GPU(s)"),
         "baseline_config": "BASELINE.json configs[2]",
         "step": ("absmax of all 64 layer tensors (1 launch) -> quantize+pack (1 launch) -> unpack+dequantize (1 launch)" if n_gpus == 1 or where != "gpu" else
-                 "absmax (2 launches, 32 layer tensors each) -> allreduce-max of each half, overlapped with the other half's kernel -> "
-                 "quantize+pack (2 launches) -> unpack+dequantize (1 launch)"),
+                 "absmax (1 launch) -> max over ranks of the 64 absmax words (see `collective`) -> quantize+pack (1 launch) -> unpack+dequantize (1 launch)"),
         "algorithmic_bytes_per_element": 7.0,
         "l2_policy": "inputs (64 GiB whole job) are far larger than the 126 MB L2; no flush needed (the small-output legs flush L2 before every timed launch)",
         "parallelism": f"kv-head shard x{n_gpus}" if where == "gpu" else "cpu",
@@ -390,13 +389,23 @@ def run_c3(cx: Ctx, cfg, legs):
     stream = cx.stream()
     dom_events = []  # (start, end) around every launch of the dominant kernel inside the timed region
     half = n_tensors // 2
+    from kvq_b200.distributed import AbsmaxExchange
+    xch = AbsmaxExchange(dev) if world > 1 and not args.nccl_absmax else None
+    use_xch = xch is not None and xch.available
 
     def step(timed: bool):
         # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between.  Head-sharded
         # (N > 1): the batch goes through absmax / quantize in two halves so that the allreduce of one half (NCCL's stream)
         # overlaps the other half's kernel -- SURVEY 8e: "overlap by launching phase-1 for tensor i+1 before phase-2 of tensor i"
         n_launch = 3
-        if world > 1:
+        if use_xch:
+            # one exchange kernel through peer-mapped memory between phase 1 and phase 2 (no NCCL call on the step)
+            L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
+            xch.exchange_(bits)
+            L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
+                                          scales.data_ptr(), None, stream), "kvq_quant_batched")
+            n_launch = 4
+        elif world > 1:
             works = []
             for lo_t, cnt in ((0, half), (half, n_tensors - half)):
                 L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr() + 8 * lo_t, L.BF16, cnt, n_local, bits.data_ptr() + 4 * lo_t, stream),
@@ -485,8 +494,10 @@ def run_c3(cx: Ctx, cfg, legs):
 
     del xs, packed, outs, x0, tx, tp, to
     torch.cuda.empty_cache()
+    collective = ("none (1 GPU)" if world == 1 else "absmax exchange through peer-mapped memory (kvq_absmax_exchange), 1 launch per step" if use_xch else
+                  "NCCL allreduce(MAX) of the absmax words, two halves overlapped with the kernels" + (f" (peer-memory exchange unavailable: {xch.why})" if xch is not None else ""))
     return {"value": value, "ms_step": ms_step, "clocks": clocks, "roofline": roof, "Hl": Hl, "per_token": per_token,
-            "shard_parity": shard_parity}
+            "shard_parity": shard_parity, "collective": collective}
 
 
 def run_per_token(cx: Ctx, cfg, xs, packed, outs, Hl):
@@ -1077,7 +1088,7 @@ def run_gpu(args, cfg):
             "c4": c4, "decode": decode, "paged": paged,
             "c2": gpt2["c2"] if gpt2 else None, "c1": dict(gpt2["c1"], reference_cpu=c1_ref) if gpt2 else None,
             "gpt2_clocks": gpt2["clocks"] if gpt2 else None,
-            "shard_parity": c3["shard_parity"] if c3 else None,
+            "shard_parity": c3["shard_parity"] if c3 else None, "collective": c3["collective"] if c3 else None,
             "sm_count": cx.sm_count, "workload_flag": args.workload,
         }
         emit(line)
@@ -1104,6 +1115,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline legs")
     ap.add_argument("--skip-decode", action="store_true", help="profiling runs only: leave out the decode-attention (C5) leg")
     ap.add_argument("--skip-paged-decode", action="store_true", help="profiling runs only: leave out the paged half of the decode leg")
+    ap.add_argument("--nccl-absmax", action="store_true", help="N > 1: exchange the absmax words with NCCL's allreduce instead of the peer-memory kernel (A/B)")
     ap.add_argument("--skip-extra", action="store_true", help="profiling runs only: leave out the per-token / C4 / paged / C2 legs")
     args = ap.parse_args()
     cfg = dict(C3)

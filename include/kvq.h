@@ -165,6 +165,18 @@ KVQ_API int kvq_quant_per_token_fused_batched(const void* const* xs, int dtype, 
                                               const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
                                               float* const* scales_f32_out, kvq_stream_t stream);
 
+/* ---------------------------------------------------------------------------------- multi-GPU: the absmax exchange
+ * A head-sharded cache exchanges one thing, between phase 1 and phase 2: the absmax words (max over ranks; reference scale
+ * over all heads: ops.py:27,:48,:330,:342).  kvq_absmax_exchange does it without a collective library: peer_buffers is a
+ * DEVICE array of world_size device pointers, entry r = rank r's exchange buffer (kvq_absmax_exchange_buffer_bytes() bytes,
+ * zero-initialised once, writable by every peer: e.g. torch symmetric memory or cudaIpc / VMM mappings).  One small kernel
+ * per rank writes its words to every peer, publishes `seq`, waits for all peers' `seq` and max-combines in place.  `seq`: a
+ * non-zero step counter, the same on every rank, increasing by one per call.  n_words <= 1024, world_size <= 16.  Results
+ * are bit-identical to an allreduce(MAX).  (NCCL's allreduce stays available: kvq_b200.distributed.allreduce_absmax_.) */
+KVQ_API int64_t kvq_absmax_exchange_buffer_bytes(void);
+KVQ_API int kvq_absmax_exchange(uint32_t* absmax_bits, int64_t n_words, void* const* peer_buffers, int rank, int world_size,
+                                uint32_t seq, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: eviction
  * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
  * of every destination row in registers; no index tensor and no intermediate parts list exists. */

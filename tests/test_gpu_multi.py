@@ -62,6 +62,19 @@ def _worker(rank, world, port, ret):
             a = kvq_b200.decode_attention_quantized(qm.contiguous(), kc, ks, kb, vc, vs, vb, variant=variant)
             b = kvq_b200.decode_attention_quantized(q.cuda(), fk, fks, kb, fv, fvs, vb, variant=variant)[:, rank * 4 * Hl:(rank + 1) * 4 * Hl]
             ok[f"attention {variant}"] = torch.equal(a, b)
+        # the peer-memory absmax exchange (csrc/xchg.cu) equals the NCCL allreduce(MAX), for many steps in a row
+        from kvq_b200.distributed import AbsmaxExchange, allreduce_absmax_
+        ex = AbsmaxExchange(torch.device("cuda", rank))
+        ok["exchange available: " + ex.why] = ex.available
+        same = True
+        for step in range(50):
+            gg = torch.Generator(device="cuda").manual_seed(1000 * step + rank)
+            words = torch.randint(0, 2 ** 31 - 1, (64,), device="cuda", generator=gg, dtype=torch.int64).to(torch.int32)
+            a, b2 = words.clone(), words.clone()
+            ex.exchange_(a)
+            allreduce_absmax_(b2, True)
+            same &= bool(torch.equal(a, b2))
+        ok["exchange == allreduce"] = same
         # head-sharded PAGED store (VERDICT r1 missing #5): same codes / scales through the block table, same attention
         paged = kvq_b200.PagedQuantizedLayerKV("mixed", block_size=64, compute_dtype=torch.bfloat16, group=True)
         paged.append_tokens(mine[:, :, :200], vmine[:, :, :200])
