@@ -392,6 +392,10 @@ def run_c3(cx: Ctx, cfg, legs):
     from kvq_b200.distributed import AbsmaxExchange
     xch = AbsmaxExchange(dev) if world > 1 and not args.nccl_absmax else None
     use_xch = xch is not None and xch.available
+    if use_xch:
+        side = torch.cuda.Stream(dev, priority=-1)
+        ev_abs, ev_x = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+        bits_halves = [bits[:half], bits[half:]]
 
     def step(timed: bool):
         # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between.  Head-sharded
@@ -399,12 +403,24 @@ def run_c3(cx: Ctx, cfg, legs):
         # overlaps the other half's kernel -- SURVEY 8e: "overlap by launching phase-1 for tensor i+1 before phase-2 of tensor i"
         n_launch = 3
         if use_xch:
-            # one exchange kernel through peer-mapped memory between phase 1 and phase 2 (no NCCL call on the step)
-            L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits.data_ptr(), stream), "kvq_absmax_batched")
-            xch.exchange_(bits)
-            L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8, tp.ptrs.data_ptr(),
-                                          scales.data_ptr(), None, stream), "kvq_quant_batched")
-            n_launch = 4
+            # the exchange kernel (peer-mapped memory, no NCCL call on the step) runs on a high-priority side stream: the batch
+            # goes through absmax / quantize in two halves so that the wait for the slowest rank's words of one half hides
+            # behind the other half's kernel
+            main = torch.cuda.current_stream(dev)
+            for i, (lo_t, cnt) in enumerate(((0, half), (half, n_tensors - half))):
+                L.check(lib.kvq_absmax_batched(tx.ptrs.data_ptr() + 8 * lo_t, L.BF16, cnt, n_local, bits.data_ptr() + 4 * lo_t, stream),
+                        "kvq_absmax_batched")
+                ev_abs[i].record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_abs[i])
+                    xch.exchange_(bits_halves[i])
+                    ev_x[i].record(side)
+            for i, (lo_t, cnt) in enumerate(((0, half), (half, n_tensors - half))):
+                main.wait_event(ev_x[i])
+                L.check(lib.kvq_quant_batched(tx.ptrs.data_ptr() + 8 * lo_t, L.BF16, cnt, n_local, 4 | L.ABSMAX_COVERS_INPUT,
+                                              bits.data_ptr() + 4 * lo_t, 1e-8, tp.ptrs.data_ptr() + 8 * lo_t,
+                                              scales.data_ptr() + 2 * lo_t, None, stream), "kvq_quant_batched")
+            n_launch = 7
         elif world > 1:
             works = []
             for lo_t, cnt in ((0, half), (half, n_tensors - half)):
@@ -494,7 +510,7 @@ def run_c3(cx: Ctx, cfg, legs):
 
     del xs, packed, outs, x0, tx, tp, to
     torch.cuda.empty_cache()
-    collective = ("none (1 GPU)" if world == 1 else "absmax exchange through peer-mapped memory (kvq_absmax_exchange), 1 launch per step" if use_xch else
+    collective = ("none (1 GPU)" if world == 1 else "absmax exchange through peer-mapped memory (kvq_absmax_exchange) on a side stream, two halves overlapped with the kernels" if use_xch else
                   "NCCL allreduce(MAX) of the absmax words, two halves overlapped with the kernels" + (f" (peer-memory exchange unavailable: {xch.why})" if xch is not None else ""))
     return {"value": value, "ms_step": ms_step, "clocks": clocks, "roofline": roof, "Hl": Hl, "per_token": per_token,
             "shard_parity": shard_parity, "collective": collective}
