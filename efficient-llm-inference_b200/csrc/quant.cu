@@ -360,13 +360,18 @@ struct TokBatch {
     int64_t row_off;  // tokens
 };
 
-template <int DT, int BITS, int NV, int MODE>
+// TPT: threads per token.  256: one token per CTA at a time (block-wide max).  32 / 64 / 128: 8 / 4 / 2 tokens per CTA at a time,
+// each owned by TPT threads -- for small tokens (a head shard at N = 8 is 4 KB per token: one vector per thread and two block
+// barriers per 4 KB with TPT = 256; with TPT = 32 a warp owns the token, eight vectors per lane, and the max is a REDUX).
+template <int DT, int BITS, int NV, int MODE, int TPT = kThreads>
 __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __restrict__ x, RowGeom g, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out,
                                                               uint32_t* __restrict__ absmax_out, int accumulate,
                                                               TokBatch tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
     __shared__ uint32_t red[kThreads / 32];
+    static_assert(TPT == kThreads || (NV > 0 && (TPT == 32 || TPT == 64 || TPT == 128)), "TPT");
+    constexpr int TOKS = kThreads / TPT;   // tokens in flight per CTA
     if (tb.xs) {
         x = reinterpret_cast<const char*>(tb.xs[blockIdx.y]);
         q = reinterpret_cast<char*>(tb.qs[blockIdx.y]) + tb.row_off * g.qT;
@@ -380,6 +385,7 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
     // without; INT4 5 410 with vs 5 950 without.
     constexpr bool kFusedClamp = BITS == 8;
     const int n_vec = g.nP * g.vpr;
+    const int u = TPT == kThreads ? threadIdx.x : threadIdx.x % TPT, slot = TPT == kThreads ? 0 : threadIdx.x / TPT;
 
     // per-thread vector -> (plane, column) offsets do not depend on the token: compute them once
     // (32-bit byte offsets: the host only picks NV > 0 when they fit)
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
     if (NV > 0) {
 #pragma unroll
         for (int k = 0; k < kNV; ++k) {
-            const int j = threadIdx.x + k * kThreads;
+            const int j = u + k * TPT;
             xoff[k] = kNone; qoff[k] = 0;
             if (j < n_vec) {
                 const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
@@ -399,14 +405,16 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
             }
         }
     }
-    for (int64_t t = blockIdx.x; t < g.T; t += gridDim.x) {
+    for (int64_t t0 = (int64_t)blockIdx.x * TOKS; t0 < g.T; t0 += (int64_t)gridDim.x * TOKS) {
+        const int64_t t = t0 + slot;
+        const bool live = t < g.T;   // (always true for TPT == kThreads)
         const char* xt = x + t * g.xT;
         char* qt = q + t * g.qT;
         uint4 v[kNV];
         uint32_t m = 0;
         if (NV > 0) {
 #pragma unroll
-            for (int k = 0; k < kNV; ++k) v[k] = xoff[k] != kNone ? ld_stream(xt + xoff[k]) : make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < kNV; ++k) v[k] = (live && xoff[k] != kNone) ? ld_stream(xt + xoff[k]) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < kNV; ++k) m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(v[k]));
         } else {
@@ -417,20 +425,31 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
                 m = InVec<DT>::combine(m, InVec<DT>::absmax_bits(ld_stream(xt + xo + (int64_t)c * 16)));
             }
         }
-        m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
-        if (threadIdx.x == 0 && absmax_out) {
+        if constexpr (TPT == kThreads) {
+            m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+        } else {
+            m = __reduce_max_sync(0xffffffffu, InVec<DT>::finish_absmax(m));
+            if constexpr (TPT > 32) {   // the token's TPT / 32 warps combine through shared memory
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+                __syncthreads();
+                const int w0 = slot * (TPT / 32);
+#pragma unroll
+                for (int w = 0; w < TPT / 32; ++w) m = max(m, red[w0 + w]);
+            }
+        }
+        if (u == 0 && live && absmax_out) {
             if (accumulate) atomicMax(absmax_out + t, m); else absmax_out[t] = m;
         }
         if (MODE == 0) {
             const Scale sc = scale_from_bits<BITS>(m, eps);
-            if (threadIdx.x == 0) {
+            if (u == 0 && live) {
                 if (scale_out) store_scalar<DT>(scale_out, t, sc.s);
                 if (scale_f32_out) scale_f32_out[t] = round_through<DT>(sc.s);
             }
             if (NV > 0) {
 #pragma unroll
                 for (int k = 0; k < kNV; ++k)
-                    if (xoff[k] != kNone) quant_store<DT, BITS, kFusedClamp>(v[k], sc, qt + qoff[k]);
+                    if (live && xoff[k] != kNone) quant_store<DT, BITS, kFusedClamp>(v[k], sc, qt + qoff[k]);
             } else {
                 for (int j = threadIdx.x; j < n_vec; j += kThreads) {
                     const int p = g.shift >= 0 ? j >> g.shift : j / g.vpr, c = j - p * g.vpr;
@@ -440,7 +459,7 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
                 }
             }
         }
-        __syncthreads();  // `red` is reused by the next token
+        if constexpr (TPT != 32) __syncthreads();  // `red` is reused by the next token
     }
 }
 
@@ -983,12 +1002,26 @@ void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const
                         void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate,
                         const TokBatch& tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
 #define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
+#define KVQ_TFT(TPT) token_fused_kernel<DT, BITS, 8, MODE, TPT><<<dim3((unsigned)tgrid, grid.y), kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
+    // small tokens, many of them: several tokens per CTA, TPT threads each (eight vectors per thread)
+    if (MODE == 0 && nv >= 1 && nv <= 4 && g.T >= 1024) {
+        const int64_t n_vec = (int64_t)g.nP * g.vpr;
+        const int tpt = n_vec <= 8 * 32 ? 32 : n_vec <= 8 * 64 ? 64 : 128;
+        const int64_t groups = (g.T + (kThreads / tpt) - 1) / (kThreads / tpt);
+        // as many BYTES per CTA as the one-token form walks (cap CTAs x one token each per sweep): cap / (tokens per CTA) CTAs
+        int64_t cap = (int64_t)sm_count() * token_ctas_per_sm() / (kThreads / tpt);
+        if (cap < 2 * sm_count()) cap = 2 * sm_count();
+        const int64_t tgrid = groups < cap ? groups : cap;
+        if (tpt == 32) KVQ_TFT(32); else if (tpt == 64) KVQ_TFT(64); else KVQ_TFT(128);
+        return;
+    }
     if (nv <= 1) KVQ_TF(1);
     else if (nv <= 2) KVQ_TF(2);
     else if (nv <= 4) KVQ_TF(4);
     else if (nv <= 8) KVQ_TF(8);
     else KVQ_TF(0);
 #undef KVQ_TF
+#undef KVQ_TFT
 }
 
 dim3 token_grid(int64_t T) {

@@ -161,3 +161,20 @@ def test_store_capacity_growth_amortises(kvq):
             copies += last is not None
             last = layer._k.codes
     assert len(layer) == 250 and copies <= 3, copies
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(16, 1, 2048, 128), (4, 2, 1500, 64), (2, 4, 1100, 128), (1, 1, 1025, 64), (3, 1, 4099, 32)])
+def test_small_tokens_several_per_cta(kvq, oracle, dtype, shape):
+    """Small tokens (a head shard at N = 8: 4 KB per token) take the several-tokens-per-CTA form of the fused per-token quantizer
+    (32 / 64 / 128 threads per token): codes and scales bit-identical to the oracle, for contiguous and strided inputs."""
+    x = gen(shape, dtype, shape[2])
+    for mode, bits in (("int8", 8), ("int4", 4)):
+        layer = kvq.QuantizedLayerKV(mode, "cuda", dtype)
+        xd = x.cuda()
+        hf = xd.transpose(1, 2).contiguous().transpose(1, 2)   # [B,T,H,D] memory viewed as [B,H,T,D]
+        layer.append_tokens(hf, xd)
+        kc, ks, _, vc, vs, _ = layer.quantized()
+        oq, osc, _ = oracle.quantize_per_token(x, bits)
+        assert torch.equal(kc.cpu(), oq) and torch.equal(vc.cpu(), oq)
+        assert torch.equal(ks.cpu(), osc.float()) and torch.equal(vs.cpu(), osc.float())

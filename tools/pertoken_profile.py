@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "efficient-llm-inference_b200"))
 from kvq_b200 import _lib as L
 bits = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-B, H, T, D = 16, 8, 32768, 128
+B, H, T, D = 16, int(sys.argv[3]) if len(sys.argv) > 3 else 8, 32768, 128
 xs = [torch.randn(B, H, T, D, device="cuda", dtype=torch.bfloat16) for _ in range(n)]
 W = D if bits == 8 else D // 2
 qs = [torch.empty(B, H, T, W, device="cuda", dtype=torch.uint8) for _ in range(n)]
