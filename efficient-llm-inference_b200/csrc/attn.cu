@@ -1,20 +1,25 @@
-// attn.cu -- area 4: decode attention over a per-token-quantized KV cache (sm_100a).
+// attn.cu -- area 4: decode attention over a per-token-quantized KV cache (sm_100a): the CUDA-core kernel family, the
+// generic any-shape kernel, the split merge, and the C entry points.  (The tensor-map TMA + INT8 MMA family: attn_mma.cu.)
 //
 // The reference dequantizes EVERY stored token, concatenates, wraps the result in a DynamicCache and
 // lets transformers run softmax(q k^T / sqrt(D)) v (src/benchmarking/benchmarker.py:470-477,
 // src/quantization/ops.py:213-269, :345-355).  Here the cache is read once, as codes: INT8 or packed
-// INT4 K/V are dequantized in registers (code * scale[t]) inside a split-K GEMV with an online
-// softmax.  No tensor cores: at decode the query is one token, so per KV head this is a
-// [G x D] . [D x T] product with G = Hq/H <= 8 rows -- bandwidth-bound streaming, not a dense GEMM.
+// INT4 K/V are dequantized in registers (code * scale[t]) inside a split-K pass with an online softmax.
 //
-// Grid (n_splits, H, B), 128 threads.  Per tile of 128 tokens:
+//   decode_attn_mha_kernel     G = Hq/H = 1: per-warp DP4A over a cp.async.bulk ring (the bandwidth-bound GEMV of north_star)
+//   decode_attn_gqa_kernel     G = 2, 4, 8: register-tiled packed FFMA2 over the same ring (FMA-bound on CUDA cores at G = 8)
+//   decode_attn_split_kernel   register-staged fp32 fallback for code rows that are not back to back
+//   decode_attn_generic_kernel any head_dim 1..512, any G, any alignment (coverage, not bandwidth)
+//   decode_attn_merge_kernel   merges the splits' partials (m, l, acc[D]) and the step's own, exact token
+//
+// Grid (n_splits, H, B); n_splits is chosen for wave efficiency (choose_splits).  The register-staged fallback, per tile of
+// 128 tokens:
 //   K phase  : a lane owns 16 consecutive d of one token (16 B of INT8 / 8 B of INT4); partial dot
 //              products are reduced over the D/16 lanes of the row by shuffles.
 //   softmax  : per query head, tile max / running max / exp2 / running sum in one warp.
 //   V phase  : a lane owns a fixed slice of 32/G consecutive d for every token of its row group and
 //              accumulates G x (32/G) fp32 partial outputs; row groups are summed through shared
 //              memory once per split.
-// Partials (m, l, acc[D]) per (b, hq, split) go to the workspace; a second kernel merges the splits.
 #include <cmath>
 
 #include "attn_common.cuh"

@@ -6,8 +6,8 @@
 // DP4A kernel still issues 5.85 instructions per (token, channel) pair (0.63).  But the codes ARE integers and both
 // contractions are tiny GEMMs per KV head --  scores[t, g] = sum_d K[t, d] q[g, d]  and  out[g, d] = sum_t w[g, t] V[t, d]
 // -- whose second operand can be made integer exactly the way the DP4A kernel already does it: q as three signed byte
-// planes (24-bit fixed point per head), the softmax weights w = p * v_scale[t] as three unsigned byte planes (24-bit fixed
-// point against max(v_scale), lazy reference).  Then one  mma.sync.m16n8k32.s32.{s8|u8}.{s8|u8}  does 4096 MACs where the
+// planes (24-bit fixed point per head), the softmax weights w = p * v_scale[t] as four unsigned byte planes (32-bit fixed
+// point against 2^8 * max(v_scale), lazy reference).  Then one  mma.sync.m16n8k32.s32.{s8|u8}.{s8|u8}  does 4096 MACs where the
 // DP4A kernel needs 1024 instructions, for any G <= 8, and the kernel is back on the HBM roofline.  north_star words decode
 // attention as "a bandwidth-bound split-K GEMV with no tensor cores, because decode at batch <= 16 is not a dense
 // contraction": at G = 8 that premise is measurably false, so this variant is offered
@@ -16,7 +16,8 @@
 // Data movement.  One elected thread streams tiles of 128 tokens with cp.async.bulk.tensor (SASS UTMALDG) from 4-D tensor maps
 // over the code tensors [row bytes, T, H, B] (5-D [row, block, H, B, n_phys] through the block table for a paged store) into
 // a ring of shared-memory stages, hardware-swizzled (128B / 64B / 32B swizzle = the row size), completing on an mbarrier
-// per stage; an `empty` mbarrier per stage (one arrival per warp) lets the producer run ahead.  The swizzle is what makes
+// per stage, together with the tile's k_scale / v_scale (two 512-byte bulk copies).  There is no producer thread: the LAST
+// warp to leave a stage (an acq_rel counter per stage) refills it at once, so the whole ring stays in flight.  The swizzle is what makes
 // the MMA fragment loads conflict-free: a fragment wants the SAME 16-byte column of 8 different token rows, and unswizzled
 // rows of 128 bytes would put all eight in the same banks.
 //
@@ -24,11 +25,12 @@
 // loop) and keeps int32 accumulators for all of D in registers:
 //   K phase : A = K codes straight from shared memory (ldmatrix; INT4 rows split into even / odd nibbles, q's fragment
 //             permuted to match), B = q byte planes, columns = (plane, head); 2 m-tiles x D/32 k-steps x ceil(3G/8) MMAs.
-//   softmax : plane sums -> fp32 score, warp max per head by shuffles, lazy reference (moves only when exceeded by 2^3),
-//             exp2, weight -> three bytes, exchanged through a 1 KB per-warp patch of shared memory in A-fragment order.
+//   softmax : plane sums -> fp32 score, warp max per head by shuffles, lazy reference (moves only when exceeded by 2^8),
+//             exp2, weight -> 32-bit fixed point = four bytes, exchanged through a 1 KB per-warp patch of shared memory in
+//             A-fragment order.
 //   V phase : B = V codes, four tokens' words byte-transposed in registers (8 PRMT per 16 bytes; packed INT4 is
 //             transposed first and split into nibbles after, the high nibble used in place as 16 x code), A = weight planes,
-//             rows = (plane, head); D/8 n-tiles x ceil(3G/16) MMAs per 32 tokens.
+//             rows = (plane, head); D/8 n-tiles x ceil(4G/16) MMAs per 32 tokens.
 //   flush   : int32 -> fp32 (per-warp accumulators in shared memory) only when a reference moves or the split ends.
 // The token <-> fragment-slot assignment (tok_of) is chosen so that every shared-memory access of the main loop is
 // conflict-free under the hardware swizzle and the K-phase lane that computes a weight is the lane that packs it.

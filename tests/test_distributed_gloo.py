@@ -111,3 +111,41 @@ def test_two_half_async_allreduce_equals_one_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def _worker_exchange_fallback(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kvq_b200.distributed import AbsmaxExchange
+        # no CUDA device here: symmetric memory cannot be set up, so the exchange must say why and fall back to the allreduce
+        ex = AbsmaxExchange(torch.device("cpu"), None)
+        bits = torch.tensor([1.0 + rank, 7.0 - 3 * rank, 0.0], dtype=torch.float32).view(torch.int32).clone()
+        out = ex.exchange_(bits)
+        want = torch.tensor([float(world), 7.0, 0.0], dtype=torch.float32).view(torch.int32)
+        q.put((rank, bool(not ex.available and ex.why and out is bits and torch.equal(bits, want))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_absmax_exchange_falls_back_to_allreduce_without_symmetric_memory():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_exchange_fallback, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_absmax_exchange_single_rank_is_identity():
+    from kvq_b200.distributed import AbsmaxExchange
+    ex = AbsmaxExchange(torch.device("cpu"), None)
+    b = torch.tensor([3], dtype=torch.int32)
+    assert not ex.available and ex.why == "single rank" and ex.exchange_(b) is b

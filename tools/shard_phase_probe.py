@@ -1,6 +1,6 @@
 """Per-phase time of the C3 step on ONE GPU at the per-rank shard shapes of N = 1, 2, 4, 8 (same bytes per launch as a rank of
 the N-GPU run sees; 64 tensors each): shows which phase loses efficiency when the tensors get small.
-   python tools/shard_phase_probe.py [heads ...]      (KVQ_FLAT_MIN_CPC etc. apply)"""
+   python tools/shard_phase_probe.py [heads ...]      (launch-shape knobs are compile-time macros: -DKVQ_FLAT_MIN_CPC=... etc.)"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
