@@ -184,6 +184,13 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+        if self.world > 1:
+            # the hosts leave the barrier up to a millisecond apart; a stream-ordered (not host-synchronised) tiny allreduce makes the
+            # DEVICE timelines start together: every rank's next event is recorded when this kernel ends, which it does on all
+            # ranks at once.  Without it the early ranks' timed regions include the wait for the late ones' first step.
+            if not hasattr(self, "_align"):
+                self._align = self.torch.zeros(1, device=self.dev)
+            self.dist.all_reduce(self._align)
 
     def max_over_ranks(self, ms: float) -> float:
         if self.world == 1:
@@ -388,11 +395,14 @@ def run_c3(cx: Ctx, cfg, legs):
     tx, tp, to = TensorTable(xs), TensorTable(packed), TensorTable(outs)
     stream = cx.stream()
     dom_events = []  # (start, end) around every launch of the dominant kernel inside the timed region
+    front_events = []  # (start, end) around absmax -> exchange -> quantize of every timed step
     half = n_tensors // 2
     from kvq_b200.distributed import AbsmaxExchange
     xch = AbsmaxExchange(dev) if world > 1 and not args.nccl_absmax else None
     use_xch = xch is not None and xch.available
-    if use_xch:
+    use_fused = use_xch and not args.side_stream_exchange
+    bits_local = torch.zeros(n_tensors, dtype=torch.int32, device=dev)
+    if use_xch and not use_fused:
         side = torch.cuda.Stream(dev, priority=-1)
         ev_abs, ev_x = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
         bits_halves = [bits[:half], bits[half:]]
@@ -402,8 +412,21 @@ def run_c3(cx: Ctx, cfg, legs):
         # (N > 1): the batch goes through absmax / quantize in two halves so that the allreduce of one half (NCCL's stream)
         # overlaps the other half's kernel -- SURVEY 8e: "overlap by launching phase-1 for tensor i+1 before phase-2 of tensor i"
         n_launch = 3
-        if use_xch:
-            # the exchange kernel (peer-mapped memory, no NCCL call on the step) runs on a high-priority side stream: the batch
+        if timed:
+            e_in = torch.cuda.Event(enable_timing=True)
+            e_in.record()
+        if use_fused:
+            # the exchange lives INSIDE the two kernels: the absmax kernel's last CTA per tensor stores the word into every rank's
+            # peer-mapped buffer, the quantize kernel's CTAs gather the world's words of their tensor in the prologue.  Three
+            # launches per step like the 1-GPU step, one stream, no collective call.
+            seq = xch.next_fused_seq()
+            L.check(lib.kvq_absmax_batched_publish(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, bits_local.data_ptr(), xch.peer_table_ptr,
+                                                   xch.rank, xch.world, seq, stream), "kvq_absmax_batched_publish")
+            L.check(lib.kvq_quant_batched_gather(tx.ptrs.data_ptr(), L.BF16, n_tensors, n_local, 4 | L.ABSMAX_COVERS_INPUT, bits.data_ptr(), 1e-8,
+                                                 tp.ptrs.data_ptr(), scales.data_ptr(), None, xch.local_buffer_ptr, xch.world, seq, stream),
+                    "kvq_quant_batched_gather")
+        elif use_xch:
+            # A/B (--side-stream-exchange): the exchange kernel (peer-mapped memory, no NCCL call on the step) runs on a high-priority side stream: the batch
             # goes through absmax / quantize in two halves so that the wait for the slowest rank's words of one half hides
             # behind the other half's kernel
             main = torch.cuda.current_stream(dev)
@@ -440,6 +463,7 @@ def run_c3(cx: Ctx, cfg, legs):
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            front_events.append((e_in, e0))
         L.check(lib.kvq_dequant_batched(tp.ptrs.data_ptr(), 4, n_tensors, n_local, scales.data_ptr(), L.BF16, to.ptrs.data_ptr(),
                                         L.BF16, stream), "kvq_dequant_batched")
         if timed:
@@ -459,7 +483,18 @@ def run_c3(cx: Ctx, cfg, legs):
     ev1.record()
     cx.sync_all()
     clocks = sampler.stop()
+    my_ms = ev0.elapsed_time(ev1) / args.steps
     ms_step = cx.max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    # per-rank view (explains the scaling figure): every rank's own ms per step, and its absmax -> exchange -> quantize / dequantize split
+    mine = torch.tensor([my_ms, statistics.mean(a.elapsed_time(b) for a, b in front_events),
+                         statistics.mean(a.elapsed_time(b) for a, b in dom_events)], device=dev)
+    if world > 1:
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = {"ms_per_step": [round(float(t[0]), 4) for t in allr], "absmax_exchange_quant_ms": [round(float(t[1]), 4) for t in allr],
+                "dequant_ms": [round(float(t[2]), 4) for t in allr]}
     job_bytes = 7.0 * n_global * n_tensors
     value = job_bytes / (ms_step * 1e-3) / 1e9
     cx.launches += launches
@@ -510,10 +545,13 @@ def run_c3(cx: Ctx, cfg, legs):
 
     del xs, packed, outs, x0, tx, tp, to
     torch.cuda.empty_cache()
-    collective = ("none (1 GPU)" if world == 1 else "absmax exchange through peer-mapped memory (kvq_absmax_exchange) on a side stream, two halves overlapped with the kernels" if use_xch else
+    collective = ("none (1 GPU)" if world == 1 else
+                  "absmax words published into every rank's peer-mapped buffer by the absmax kernel's last CTA per tensor and gathered in the quantize "
+                  "kernel's prologue (kvq_absmax_batched_publish / kvq_quant_batched_gather): no collective launch, 3 launches per step" if use_fused else
+                  "absmax exchange through peer-mapped memory (kvq_absmax_exchange) on a side stream, two halves overlapped with the kernels" if use_xch else
                   "NCCL allreduce(MAX) of the absmax words, two halves overlapped with the kernels" + (f" (peer-memory exchange unavailable: {xch.why})" if xch is not None else ""))
     return {"value": value, "ms_step": ms_step, "clocks": clocks, "roofline": roof, "Hl": Hl, "per_token": per_token,
-            "shard_parity": shard_parity, "collective": collective}
+            "shard_parity": shard_parity, "collective": collective, "per_rank": per_rank}
 
 
 def run_per_token(cx: Ctx, cfg, xs, packed, outs, Hl):
@@ -1105,6 +1143,7 @@ def run_gpu(args, cfg):
             "c2": gpt2["c2"] if gpt2 else None, "c1": dict(gpt2["c1"], reference_cpu=c1_ref) if gpt2 else None,
             "gpt2_clocks": gpt2["clocks"] if gpt2 else None,
             "shard_parity": c3["shard_parity"] if c3 else None, "collective": c3["collective"] if c3 else None,
+            "per_rank": c3["per_rank"] if c3 else None,
             "sm_count": cx.sm_count, "workload_flag": args.workload,
         }
         emit(line)
@@ -1131,6 +1170,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline legs")
     ap.add_argument("--skip-decode", action="store_true", help="profiling runs only: leave out the decode-attention (C5) leg")
     ap.add_argument("--skip-paged-decode", action="store_true", help="profiling runs only: leave out the paged half of the decode leg")
+    ap.add_argument("--side-stream-exchange", action="store_true", help="N > 1: the stand-alone exchange kernel on a side stream, two halves (A/B against the fused publish / gather form)")
     ap.add_argument("--nccl-absmax", action="store_true", help="N > 1: exchange the absmax words with NCCL's allreduce instead of the peer-memory kernel (A/B)")
     ap.add_argument("--skip-extra", action="store_true", help="profiling runs only: leave out the per-token / C4 / paged / C2 legs")
     args = ap.parse_args()

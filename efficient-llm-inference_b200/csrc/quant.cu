@@ -179,10 +179,29 @@ __device__ __forceinline__ void flat_split(const FlatWork& w, int& ti, int64_t& 
     else { c0 = b; c1 = w.chunks; }
 }
 
+// Head-sharded form of the absmax -> quantize pair WITHOUT a collective launch between them (the one exchange of the path,
+// ops.py:27,:48: the scale is over all heads).  The LAST CTA of a tensor in the absmax kernel (arrival counter per tensor)
+// stores the tensor's finished word, tagged with the step's sequence number, straight into every rank's peer-mapped buffer
+// (one 8-byte NVLink store per peer); the quantize kernel's CTAs of that tensor wait in their prologue until all ranks' words
+// for this step are there and max-combine them.  The absmax kernel waits for nobody, so there is no cycle; a peer may lag by
+// almost a whole absmax phase before anyone stalls (tensor i's word is published when 1/n of the kernel has run, and is
+// needed when the consumer's quantize reaches tensor i).  Two parities: a rank can be at most one step ahead of the slowest
+// (its step s + 1 quantize needs everyone's s + 1 words, which are published after their step s quantize).
+struct Publish {
+    void* const* peers = nullptr;   // device array of `world` peer-mapped buffer pointers (nullptr: single rank, plain kernel)
+    int rank = 0, world = 1;
+    uint32_t seq = 0;
+};
+struct Gather {
+    void* mine = nullptr;           // this rank's buffer (nullptr: absmax_bits already holds the final words)
+    int world = 1;
+    uint32_t seq = 0;
+};
+
 template <int DT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __restrict__ x, int64_t n_vec,
                                                                uint32_t* __restrict__ absmax_bits, FlatWork w,
-                                                               const void* const* __restrict__ xs = nullptr) {
+                                                               const void* const* __restrict__ xs = nullptr, Publish pub = Publish()) {
     __shared__ uint32_t red[kThreads / 32];
     int ti; int64_t c0, c1;
     flat_split(w, ti, c0, c1);
@@ -202,6 +221,21 @@ __global__ void __launch_bounds__(kThreads) absmax_flat_kernel(const uint4* __re
     m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
     // thousands of CTAs per tensor: only those that can still raise the max touch the atomic
     if (threadIdx.x == 0 && m > *reinterpret_cast<volatile uint32_t*>(absmax_bits + ti)) atomicMax(absmax_bits + ti, m);
+    if (pub.peers) {
+        __shared__ int last;
+        uint32_t* arrive = xch_arrive(pub.peers[pub.rank]);
+        if (threadIdx.x == 0) {
+            __threadfence();   // my atomicMax before my arrival
+            last = atomicAdd(arrive + ti, 1u) == (uint32_t)w.bpt - 1u;
+        }
+        __syncthreads();
+        if (last && threadIdx.x < pub.world) {
+            __threadfence();   // everyone's atomicMax before my read
+            const uint32_t word = atomicOr(absmax_bits + ti, 0u);
+            st_release_sys_u64(xch_tagged(pub.peers[threadIdx.x], (int)(pub.seq & 1u), pub.rank, ti), ((unsigned long long)pub.seq << 32) | word);
+            if (threadIdx.x == 0) arrive[ti] = 0;   // ready for the next launch (stream order)
+        }
+    }
 }
 
 template <int DT, int BITS, int UNROLL, bool CLAMP>
@@ -210,13 +244,39 @@ __global__ void __launch_bounds__(kThreads) quant_flat_kernel(const uint4* __res
                                                               char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out, FlatWork w,
                                                               const void* const* __restrict__ xs = nullptr,
-                                                              void* const* __restrict__ qs = nullptr) {
+                                                              void* const* __restrict__ qs = nullptr, Gather gat = Gather(),
+                                                              uint32_t* __restrict__ absmax_out = nullptr) {
     constexpr int kOut = OutBytes<DT, BITS>::value;
     int ti; int64_t c0, c1;
     flat_split(w, ti, c0, c1);
     const uint4* xt = xs ? reinterpret_cast<const uint4*>(xs[ti]) : x;
     char* qt = xs ? reinterpret_cast<char*>(qs[ti]) : q;
-    const Scale sc = scale_from_bits<BITS>(absmax_bits[ti], eps);
+    uint32_t word;
+    if (gat.mine) {
+        // every rank's word of this tensor for this step (written by the peers' absmax kernels), max-combined
+        __shared__ uint32_t combined;
+        if (threadIdx.x < 32) {
+            uint32_t v = 0;
+            if ((int)threadIdx.x < gat.world) {
+                const unsigned long long* slot = xch_tagged(gat.mine, (int)(gat.seq & 1u), (int)threadIdx.x, ti);
+                unsigned long long t, spins = 0;
+                while ((uint32_t)((t = ld_acquire_sys_u64(slot)) >> 32) != gat.seq) {
+                    if (++spins > (1ull << 24)) __trap();   // a peer that never publishes: fail instead of hanging the GPU (~10 s)
+                    __nanosleep(spins < 64 ? 0 : 500);
+                }
+                v = (uint32_t)t;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (threadIdx.x == 0) combined = v;
+        }
+        __syncthreads();
+        word = combined;
+        if (c0 == 0 && threadIdx.x == 0 && absmax_out) absmax_out[ti] = word;
+    } else {
+        word = absmax_bits[ti];
+    }
+    const Scale sc = scale_from_bits<BITS>(word, eps);
     if (c0 == 0 && threadIdx.x == 0) {
         if (scale_out) store_scalar<DT>(scale_out, ti, sc.s);
         if (scale_f32_out) scale_f32_out[ti] = round_through<DT>(sc.s);
@@ -1189,8 +1249,16 @@ extern "C" int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shap
 // per-tensor kernels last 20-30 us and launch gaps dominate.  Pointer tables live on the device.
 
 
-extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
-                                  kvq_stream_t stream) {
+static int check_exchange_args(void* const* peer_buffers, int rank, int world_size, uint32_t seq, int64_t n_tensors) {
+    KVQ_REQUIRE(peer_buffers, "null pointer");
+    KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld && rank >= 0 && rank < world_size, "bad rank / world size");
+    KVQ_REQUIRE(n_tensors <= kXchMaxWords, "publish / gather: at most %d tensors per call (got %lld)", kXchMaxWords, (long long)n_tensors);
+    KVQ_REQUIRE(seq != 0, "seq must be a non-zero step counter, the same on every rank (buffers start zeroed)");
+    return KVQ_OK;
+}
+
+static int run_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits, Publish pub,
+                              kvq_stream_t stream) {
     KVQ_REQUIRE(xs && absmax_bits, "null pointer");
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     KVQ_REQUIRE(n_tensors >= 0 && n_tensors <= 65535 && numel >= 0, "bad sizes");
@@ -1204,14 +1272,27 @@ extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_te
     constexpr int U = 8;
     FlatWork w; unsigned grid;
     flat_work(n_vec, U, 0, n_tensors, w, grid);
-    KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, absmax_bits, w, xs));
+    KVQ_DISPATCH_DT(dtype, absmax_flat_kernel<DT, U><<<grid, kThreads, 0, st>>>(nullptr, n_vec, absmax_bits, w, xs, pub));
     return check_launch("absmax_batched");
 }
 
-extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
-                                 const uint32_t* absmax_bits, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
-                                 kvq_stream_t stream) {
-    KVQ_REQUIRE(xs && qs && absmax_bits, "null pointer");
+extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
+                                  kvq_stream_t stream) {
+    return run_absmax_batched(xs, dtype, n_tensors, numel, absmax_bits, Publish(), stream);
+}
+
+extern "C" int kvq_absmax_batched_publish(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
+                                          void* const* peer_buffers, int rank, int world_size, uint32_t seq, kvq_stream_t stream) {
+    if (int rc = check_exchange_args(peer_buffers, rank, world_size, seq, n_tensors)) return rc;
+    KVQ_REQUIRE(numel > 0 || n_tensors == 0, "publish: empty tensors publish nothing (every rank must publish every step)");
+    Publish pub; pub.peers = peer_buffers; pub.rank = rank; pub.world = world_size; pub.seq = seq;
+    return run_absmax_batched(xs, dtype, n_tensors, numel, absmax_bits, pub, stream);
+}
+
+static int run_quant_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                             const uint32_t* absmax_bits, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                             Gather gat, uint32_t* absmax_out, kvq_stream_t stream) {
+    KVQ_REQUIRE(xs && qs && (absmax_bits || gat.mine), "null pointer");
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
     const bool covers = (bits & KVQ_ABSMAX_COVERS_INPUT) != 0 && eps == 1e-8f;
     bits &= ~KVQ_ABSMAX_COVERS_INPUT;
@@ -1226,11 +1307,28 @@ extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_ten
     FlatWork w; unsigned grid;
     flat_work(n_vec, U, 1, n_tensors, w, grid);
 #define KVQ_QB(BITS, CL) KVQ_DISPATCH_DT(dtype, quant_flat_kernel<DT, BITS, U, CL><<<grid, kThreads, 0, st>>>( \
-                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, w, xs, qs))
+                                   nullptr, n_vec, absmax_bits, eps, nullptr, scale_out, scale_f32_out, w, xs, qs, gat, absmax_out))
     if (bits == 8) { if (covers) { KVQ_QB(8, false); } else { KVQ_QB(8, true); } }
     else { if (covers) { KVQ_QB(4, false); } else { KVQ_QB(4, true); } }
 #undef KVQ_QB
     return check_launch("quant_batched");
+}
+
+extern "C" int kvq_quant_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                                 const uint32_t* absmax_bits, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                                 kvq_stream_t stream) {
+    return run_quant_batched(xs, dtype, n_tensors, numel, bits, absmax_bits, eps, qs, scale_out, scale_f32_out, Gather(), nullptr, stream);
+}
+
+extern "C" int kvq_quant_batched_gather(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                                        uint32_t* absmax_bits_out, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                                        void* local_buffer, int world_size, uint32_t seq, kvq_stream_t stream) {
+    KVQ_REQUIRE(local_buffer, "null pointer");
+    KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld, "bad world size");
+    KVQ_REQUIRE(n_tensors <= kXchMaxWords, "publish / gather: at most %d tensors per call (got %lld)", kXchMaxWords, (long long)n_tensors);
+    KVQ_REQUIRE(seq != 0, "seq must be the step counter given to kvq_absmax_batched_publish");
+    Gather gat; gat.mine = local_buffer; gat.world = world_size; gat.seq = seq;
+    return run_quant_batched(xs, dtype, n_tensors, numel, bits, nullptr, eps, qs, scale_out, scale_f32_out, gat, absmax_bits_out, stream);
 }
 
 extern "C" int kvq_dequant_batched(const void* const* codes, int bits, int64_t n_tensors, int64_t numel, const void* scales,

@@ -20,13 +20,6 @@
 namespace kvq {
 namespace {
 
-constexpr int kXchMaxWords = 1024;   // words per rank per parity
-constexpr int kXchMaxWorld = 16;
-
-// layout of one rank's buffer (uint32 units): words [2][world_max][kXchMaxWords], then flags [2][world_max]
-__host__ __device__ inline size_t xch_word_off(int parity, int src_rank, int i) { return ((size_t)parity * kXchMaxWorld + src_rank) * kXchMaxWords + i; }
-__host__ __device__ inline size_t xch_flag_off(int parity, int src_rank) { return (size_t)2 * kXchMaxWorld * kXchMaxWords + (size_t)parity * kXchMaxWorld + src_rank; }
-
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -68,7 +61,7 @@ __global__ void __launch_bounds__(256) absmax_exchange_kernel(uint32_t* __restri
 
 using namespace kvq;
 
-extern "C" int64_t kvq_absmax_exchange_buffer_bytes(void) { return (int64_t)(2 * kXchMaxWorld * kXchMaxWords + 2 * kXchMaxWorld) * 4; }
+extern "C" int64_t kvq_absmax_exchange_buffer_bytes(void) { return (int64_t)kXchBufferBytes; }
 
 extern "C" int kvq_absmax_exchange(uint32_t* absmax_bits, int64_t n_words, void* const* peer_buffers, int rank, int world_size, uint32_t seq,
                                    kvq_stream_t stream) {

@@ -64,6 +64,8 @@ SIGNATURES = {
     "kvq_chunk_mean_batched": (c_int, [c_vp, c_vp, c_i64, c_int, I64x4, I64x4, c_i64, c_i64, c_vp]),
     "kvq_absmax_exchange_buffer_bytes": (c_i64, []),
     "kvq_absmax_exchange": (c_int, [c_vp, c_i64, c_vp, c_int, c_int, ctypes.c_uint32, c_vp]),
+    "kvq_absmax_batched_publish": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_int, c_int, ctypes.c_uint32, c_vp]),
+    "kvq_quant_batched_gather": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_uint32, c_vp]),
     "kvq_evict_plan_make": (c_int, [c_int] + [c_i64] * 7 + [ctypes.POINTER(EvictPlan)]),
     "kvq_evict_indices_host": (c_int, [ctypes.POINTER(EvictPlan), c_vp]),
     "kvq_evict_indices_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),

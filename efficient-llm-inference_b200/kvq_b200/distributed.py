@@ -73,6 +73,7 @@ class AbsmaxExchange:
         from . import _lib as L
 
         self.device, self.group, self.seq, self.available, self.why = device, group, 0, False, ""
+        self.fused_seq = 0  # step counter of the publish / gather pair (its own region of the buffer)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.world == 1:
@@ -85,6 +86,7 @@ class AbsmaxExchange:
             self._buf.zero_()
             self._hdl = symm_mem.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
             self._peers = int(self._hdl.buffer_ptrs_dev)
+            self._local = self._buf.data_ptr()
             torch.cuda.synchronize(device)
             dist.barrier(group)  # every buffer zeroed before anyone's first exchange
             self.available = True
@@ -103,3 +105,17 @@ class AbsmaxExchange:
                                             L.stream_ptr(bits.device)), "kvq_absmax_exchange")
         L.count_launch()
         return bits
+
+    def next_fused_seq(self) -> int:
+        """Sequence number for one kvq_absmax_batched_publish / kvq_quant_batched_gather pair (same on every rank)."""
+        self.fused_seq += 1
+        return self.fused_seq
+
+    @property
+    def peer_table_ptr(self) -> int:
+        """Device address of the table of all ranks' buffer pointers."""
+        return self._peers
+
+    @property
+    def local_buffer_ptr(self) -> int:
+        return self._local

@@ -175,10 +175,15 @@ class TensorTable:
 
 @torch.no_grad()
 def quantize_per_tensor_batched(xs: "TensorTable", codes: "TensorTable", bits: int, scales: torch.Tensor,
-                                eps: float = 1e-8, group=None, absmax_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+                                eps: float = 1e-8, group=None, absmax_bits: Optional[torch.Tensor] = None,
+                                exchange=None) -> torch.Tensor:
     """quantize_int8_per_tensor / quantize_int4_per_tensor_packed applied to every tensor of `xs` (each with its own
-    per-tensor scale) in TWO launches total (+ one allreduce when head-sharded).  Codes go to the preallocated tensors
-    of `codes`, scale.to(x.dtype) of tensor i to scales[i].  Returns the absmax bit patterns."""
+    per-tensor scale) in TWO launches total.  Codes go to the preallocated tensors of `codes`, scale.to(x.dtype) of tensor i
+    to scales[i].  Returns the absmax bit patterns (over all ranks when head-sharded).
+
+    Head-sharded (scale over all heads, reference ops.py:27,:48): pass `group` for one NCCL allreduce(MAX) between the two
+    launches, or `exchange` (an available kvq_b200.distributed.AbsmaxExchange) for the form with NO collective launch: the
+    absmax kernel publishes each tensor's word into every rank's peer-mapped buffer and the quantize kernel gathers them."""
     n = len(xs)
     if len(codes) != n or scales.numel() < n or scales.dtype != xs.dtype:
         raise RuntimeError("codes / scales do not match the input table")
@@ -186,6 +191,19 @@ def quantize_per_tensor_batched(xs: "TensorTable", codes: "TensorTable", bits: i
         raise RuntimeError("batched INT4 needs an even last dimension")
     if absmax_bits is None:
         absmax_bits = torch.empty(n, dtype=torch.int32, device=xs.device)
+    if exchange is not None and getattr(exchange, "available", False) and xs.numel:
+        with torch.cuda.device(xs.device):
+            st, seq = L.stream_ptr(xs.device), exchange.next_fused_seq()
+            L.check(L.lib().kvq_absmax_batched_publish(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, absmax_bits.data_ptr(),
+                                                       exchange.peer_table_ptr, exchange.rank, exchange.world, seq, st),
+                    "kvq_absmax_batched_publish")
+            L.check(L.lib().kvq_quant_batched_gather(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, int(bits) | L.ABSMAX_COVERS_INPUT,
+                                                     absmax_bits.data_ptr(), float(eps), codes.ptrs.data_ptr(), scales.data_ptr(), None,
+                                                     exchange.local_buffer_ptr, exchange.world, seq, st), "kvq_quant_batched_gather")
+            L.count_launch(2)
+        return absmax_bits
+    if exchange is not None and group is None:
+        group = True if exchange.group is None else exchange.group  # exchange not available on this node: the allreduce
     with torch.cuda.device(xs.device):
         st = L.stream_ptr(xs.device)
         L.check(L.lib().kvq_absmax_batched(xs.ptrs.data_ptr(), L.dtype_code(xs.dtype), n, xs.numel, absmax_bits.data_ptr(), st),

@@ -177,6 +177,23 @@ KVQ_API int64_t kvq_absmax_exchange_buffer_bytes(void);
 KVQ_API int kvq_absmax_exchange(uint32_t* absmax_bits, int64_t n_words, void* const* peer_buffers, int rank, int world_size,
                                 uint32_t seq, kvq_stream_t stream);
 
+/* The same exchange FUSED into the two kernels it sits between (no launch, no stream hand-over for it): 
+ *   kvq_absmax_batched_publish = kvq_absmax_batched whose last CTA per tensor stores the tensor's finished word, tagged with
+ *     `seq`, into every rank's buffer (one 8-byte NVLink store per peer); absmax_bits receives the LOCAL words as before;
+ *   kvq_quant_batched_gather   = kvq_quant_batched whose CTAs first wait for all world_size words of their tensor for step
+ *     `seq` in local_buffer (= this rank's own exchange buffer) and max-combine them; absmax_bits_out (nullable) receives
+ *     the combined words.
+ * Same buffers as kvq_absmax_exchange (a separate region; the two `seq` counters are independent), same rules for `seq`
+ * (non-zero, identical on all ranks, +1 per publish/gather pair), n_tensors <= 1024.  Every rank must call both, in this
+ * order, every step; the wait is bounded (a peer that never publishes traps the kernel after ~10 s).  Codes and scales are
+ * bit-identical to the allreduce form.  Replaces the same reference lines as kvq_absmax_batched / kvq_quant_batched for a
+ * head-sharded cache (ops.py:27,:48 with the scale over all heads). */
+KVQ_API int kvq_absmax_batched_publish(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
+                                       void* const* peer_buffers, int rank, int world_size, uint32_t seq, kvq_stream_t stream);
+KVQ_API int kvq_quant_batched_gather(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, int bits,
+                                     uint32_t* absmax_bits_out, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
+                                     void* local_buffer, int world_size, uint32_t seq, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: eviction
  * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
  * of every destination row in registers; no index tensor and no intermediate parts list exists. */
