@@ -1094,39 +1094,43 @@ struct CurToken {
 };
 
 template <int ODT>
-__global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
-                                         void* __restrict__ out, CurToken cur) {
+__global__ void __launch_bounds__(1024) decode_attn_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, int n_splits, int D,
+                                                                 void* __restrict__ out, CurToken cur) {
+    // blockDim = (D rounded up to a multiple of 32, SEG): thread (d, seg) merges the splits seg, seg + SEG, ... of output d, eight
+    // independent loads per round -- with SEG = ceil(n_splits / 8) the whole workspace read is ONE round trip after the dependency
+    // wait instead of n_splits / 8 dependent ones (this kernel is on the critical path of every layer: 3-4 us of a 25 us layer at the
+    // per-GPU shapes of an 8-way head shard) -- then segment 0 folds the SEG partial results and the step's own token.
     __shared__ float dot_s[16];
+    extern __shared__ float seg_s[];  // [3][SEG - 1][blockDim.x]: M, num, den of the segments 1 ..
     const int64_t hq = blockIdx.x;
-    const int d = threadIdx.x;  // blockDim.x == D rounded up to a multiple of 32 (D <= 512)
+    const int d = threadIdx.x, seg = threadIdx.y, SEG = blockDim.y, Dp = blockDim.x;
     const bool live = d < D;
     float s_cur = -INFINITY, v_cur = 0.f;
     if (cur.k) {  // independent of the split kernel: runs before the dependency wait
         const int64_t kv_row = (hq / cur.G);  // (b * Hq + hq_in) / G == b * H + h  because Hq = G * H
-        float p = live ? load_scale(cur.q, cur.dtype, hq * D + d) * load_scale(cur.k, cur.dtype, kv_row * D + d) : 0.f;
+        float p = live && seg == 0 ? load_scale(cur.q, cur.dtype, hq * D + d) * load_scale(cur.k, cur.dtype, kv_row * D + d) : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if ((d & 31) == 0) dot_s[d >> 5] = p;
+        if (seg == 0 && (d & 31) == 0) dot_s[d >> 5] = p;
         __syncthreads();
         float tot = 0.f;
-        for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += dot_s[w];
+        for (int w = 0; w < Dp / 32; ++w) tot += dot_s[w];
         s_cur = tot * cur.qk_scale_log2;
         v_cur = live ? load_scale(cur.v, cur.dtype, kv_row * D + d) : 0.f;
     }
     // launched with programmatic stream serialization: everything above this line overlaps the split kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const float2* ml = reinterpret_cast<const float2*>(ws_ml) + hq * n_splits;
-    if (!live) return;
-    const float* acc = ws_acc + hq * n_splits * D + d;
-    float M = s_cur, num = cur.k ? v_cur : 0.f, den = cur.k ? 1.f : 0.f;
-    for (int s0 = 0; s0 < n_splits; s0 += 8) {  // 8 splits per round: independent loads, then an online-softmax merge
+    const float* acc = ws_acc + hq * n_splits * D + (live ? d : 0);
+    float M = -INFINITY, num = 0.f, den = 0.f;
+    for (int s0 = seg; s0 < n_splits; s0 += 8 * SEG) {  // 8 splits per round: independent loads, then an online-softmax merge
         float2 m8[8];
         float a8[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const bool ok = s0 + u < n_splits;
-            m8[u] = ok ? ml[s0 + u] : make_float2(-INFINITY, 0.f);
-            a8[u] = ok ? acc[(int64_t)(s0 + u) * D] : 0.f;
+            const bool ok = s0 + u * SEG < n_splits;
+            m8[u] = ok ? ml[s0 + u * SEG] : make_float2(-INFINITY, 0.f);
+            a8[u] = ok ? acc[(int64_t)(s0 + u * SEG) * D] : 0.f;
         }
         float Mn = M;
 #pragma unroll
@@ -1140,14 +1144,34 @@ __global__ void decode_attn_merge_kernel(const float* __restrict__ ws_acc, const
             den = fmaf(m8[u].y, w, den);
         }
     }
+    if (seg > 0) {
+        float* o = seg_s + (seg - 1) * Dp + d;
+        o[0] = M; o[(SEG - 1) * Dp] = num; o[2 * (SEG - 1) * Dp] = den;
+    }
+    if (SEG > 1) __syncthreads();
+    if (seg > 0 || !live) return;
+    float Mt = fmaxf(M, s_cur);
+    for (int g = 0; g < SEG - 1; ++g) Mt = fmaxf(Mt, seg_s[g * Dp + d]);
+    float w0 = M == -INFINITY ? 0.f : exp2f(M - Mt);
+    num *= w0; den *= w0;
+    if (cur.k) { const float w = exp2f(s_cur - Mt); num = fmaf(v_cur, w, num); den += w; }
+    for (int g = 0; g < SEG - 1; ++g) {
+        const float mg = seg_s[g * Dp + d];
+        const float w = mg == -INFINITY ? 0.f : exp2f(mg - Mt);
+        num = fmaf(seg_s[((SEG - 1) + g) * Dp + d], w, num);
+        den = fmaf(seg_s[(2 * (SEG - 1) + g) * Dp + d], w, den);
+    }
     store_scalar<ODT>(out, hq * D + d, num / den);
 }
 
 template <int ODT>
 int launch_merge(unsigned blocks, unsigned threads, cudaStream_t st, const float* ws_acc, const float* ws_ml, int n_splits, int D, void* out,
                  const CurToken& cur) {
+    unsigned seg = (unsigned)(n_splits + 7) / 8;
+    const unsigned seg_max = 1024u / threads < 8u ? 1024u / threads : 8u;
+    seg = seg < 1 ? 1 : seg > seg_max ? seg_max : seg;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads, seg); cfg.dynamicSmemBytes = 3 * (seg - 1) * threads * sizeof(float); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -1,11 +1,12 @@
-"""One launch pair per (variant, G) at the C5 shape for ncu captures: python tools/attn_profile.py [variant] [G ...]"""
+"""One launch pair per (variant, G) at the C5 shape for ncu captures: python tools/attn_profile.py [variant] [G ...]
+   ATTN_H=1 (KV heads: the per-rank shard of an 8-GPU run), ATTN_B, ATTN_T override the shape."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "efficient-llm-inference_b200"))
 import kvq_b200
 variant = sys.argv[1] if len(sys.argv) > 1 else "imma"
 Gs = [int(x) for x in sys.argv[2:]] or [1, 8]
-B, H, T, D = 8, 8, 65536, 128
+B, H, T, D = int(os.environ.get('ATTN_B', 8)), int(os.environ.get('ATTN_H', 8)), int(os.environ.get('ATTN_T', 65536)), 128
 g = torch.Generator(device="cuda").manual_seed(1)
 kc = torch.randint(-127, 128, (B, H, T, D), device="cuda", dtype=torch.int8, generator=g)
 vc = torch.randint(0, 256, (B, H, T, D // 2), device="cuda", dtype=torch.uint8, generator=g)
