@@ -1057,6 +1057,12 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
     return check_launch("dequant");
 }
 
+#ifndef KVQ_TOKEN_TPT_MAX_VEC
+// Tokens of at most this many 16-byte vectors (4 KB: the per-GPU token of an 8-way head shard at the C3 shape) take the
+// several-tokens-per-CTA form.  Measured on one B200, batched INT4 / INT8, bf16 (tools/pertoken_profile.py):
+//   256 vectors per token: 3.8 -> 5.9 TB/s;  512: 5.4 (this form) vs 5.9 (one token per CTA);  1024: 5.3 vs 6.4.
+#define KVQ_TOKEN_TPT_MAX_VEC 256
+#endif
 template <int DT, int BITS, int MODE>
 void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
                         void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate,
@@ -1064,7 +1070,7 @@ void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const
 #define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
 #define KVQ_TFT(TPT) token_fused_kernel<DT, BITS, 8, MODE, TPT><<<dim3((unsigned)tgrid, grid.y), kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
     // small tokens, many of them: several tokens per CTA, TPT threads each (eight vectors per thread)
-    if (MODE == 0 && nv >= 1 && nv <= 4 && g.T >= 1024) {
+    if (MODE == 0 && nv >= 1 && (int64_t)g.nP * g.vpr <= KVQ_TOKEN_TPT_MAX_VEC && g.T >= 1024) {
         const int64_t n_vec = (int64_t)g.nP * g.vpr;
         const int tpt = n_vec <= 8 * 32 ? 32 : n_vec <= 8 * 64 ? 64 : 128;
         const int64_t groups = (g.T + (kThreads / tpt) - 1) / (kThreads / tpt);
