@@ -861,9 +861,64 @@ def run_decode(cx: Ctx):
         del kp, vp
     else:
         del kcs, vcs
+    if world > 1:
+        out["append_sharded"] = run_append_sharded(cx, B, Hl, D, Lyr)
     out["clocks"] = sampler.stop()
     torch.cuda.empty_cache()
     return out
+
+
+def run_append_sharded(cx: Ctx, B, Hl, D, Lyr):
+    """The OTHER half of a head-sharded decode step: appending the step's token (K and V, INT8-K / INT4-V, one scale per token over
+    ALL heads -- ops.py:330,:342 -- hence a max over ranks) to every layer's store through QuantizedLayerKV.append.  Two forms, same
+    codes and scales: the exchange inside the quantize kernel over peer-mapped memory (one launch per tensor, what the store does
+    when symmetric memory is available) and absmax kernel -> NCCL allreduce(MAX) -> quantize kernel (the fallback).  Eager calls
+    (neither form is graph-captured here), device time of an 80-layer step, max over ranks."""
+    torch, dev = cx.torch, cx.dev
+    import kvq_b200
+    from kvq_b200 import _lib as L
+    from kvq_b200.distributed import shared_exchange
+    g = torch.Generator(device=dev).manual_seed(99 + cx.rank)
+    k1 = torch.randn(B, Hl, 1, D, device=dev, generator=g).to(torch.bfloat16)
+    v1 = torch.randn(B, Hl, 1, D, device=dev, generator=g).to(torch.bfloat16)
+    kp = torch.randn(B, Hl, 64, D, device=dev, generator=g).to(torch.bfloat16)
+    layers = [kvq_b200.QuantizedLayerKV("mixed", dev, torch.bfloat16, group=True) for _ in range(Lyr)]
+    for l in layers:
+        l.append_tokens(kp, kp)
+    have_x = shared_exchange(dev, True) is not None
+
+    def step_exchange():
+        for l in layers:
+            l.append(k1, v1)
+
+    def step_nccl():
+        for l in layers:
+            l._k.append_per_token(k1, group=True)
+            l._v.append_per_token(v1, group=True)
+
+    res = {"layers": Lyr, "tensors_per_step": 2 * Lyr, "exchange_available": have_x}
+    for name, fn in (("exchange", step_exchange), ("nccl_allreduce", step_nccl)):
+        if name == "exchange" and not have_x:
+            continue
+        for _ in range(3):
+            fn()
+        for l in layers:
+            l._k.keep_last(64), l._v.keep_last(64)
+        cx.sync_all()
+        n = 10
+        l0 = L.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        cx.sync_all()
+        cx.launches += L.launch_count - l0
+        res[name + "_ms_per_step"] = cx.max_over_ranks(e0.elapsed_time(e1) / n)
+        res[name + "_launches_per_step"] = (L.launch_count - l0) // n
+        for l in layers:
+            l._k.keep_last(64), l._v.keep_last(64)
+    return res
 
 
 # ----------------------------------------------------------------------------- e2e: host buffers through the public API

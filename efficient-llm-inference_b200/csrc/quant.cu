@@ -428,7 +428,8 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
                                                               char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out,
                                                               uint32_t* __restrict__ absmax_out, int accumulate,
-                                                              TokBatch tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
+                                                              TokBatch tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0},
+                                                              Publish xc = Publish()) {
     __shared__ uint32_t red[kThreads / 32];
     static_assert(TPT == kThreads || (NV > 0 && (TPT == 32 || TPT == 64 || TPT == 128)), "TPT");
     constexpr int TOKS = kThreads / TPT;   // tokens in flight per CTA
@@ -487,6 +488,33 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
         }
         if constexpr (TPT == kThreads) {
             m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
+            if (MODE == 0 && xc.peers) {
+                // head-sharded append in ONE kernel (kvq_quant_per_token_fused_exchange): the token's local word goes, tagged with
+                // the step number, into every rank's peer-mapped buffer; then the CTA waits for the world's words of this token
+                // and max-combines them -- the scale is over all heads (ops.py:330,:342).  Every CTA publishes before it waits and
+                // both sides walk the tokens in the same order, so the oldest unfinished token of any rank always has its peers'
+                // words published or about to be: no cycle.  The values stay in registers across the wait.
+                __shared__ uint32_t combined;
+                const int widx = (int)blockIdx.y * (int)g.T + (int)t, parity = (int)(xc.seq & 1u);
+                if ((int)threadIdx.x < xc.world)
+                    st_release_sys_u64(xch_tagged(xc.peers[threadIdx.x], parity, xc.rank, widx), ((unsigned long long)xc.seq << 32) | m);
+                if (threadIdx.x < 32) {
+                    uint32_t w = 0;
+                    if ((int)threadIdx.x < xc.world) {
+                        const unsigned long long* slot_p = xch_tagged(xc.peers[xc.rank], parity, (int)threadIdx.x, widx);
+                        unsigned long long tg, spins = 0;
+                        while ((uint32_t)((tg = ld_acquire_sys_u64(slot_p)) >> 32) != xc.seq) {
+                            if (++spins > (1ull << 24)) __trap();   // a peer that never arrives: fail instead of hanging the GPU
+                            __nanosleep(spins < 64 ? 0 : 500);
+                        }
+                        w = (uint32_t)tg;
+                    }
+                    w = __reduce_max_sync(0xffffffffu, w);
+                    if (threadIdx.x == 0) combined = w;
+                }
+                __syncthreads();
+                m = combined;
+            }
         } else {
             m = __reduce_max_sync(0xffffffffu, InVec<DT>::finish_absmax(m));
             if constexpr (TPT > 32) {   // the token's TPT / 32 warps combine through shared memory
@@ -1066,11 +1094,11 @@ int dequant(const void* codes, const int64_t shape[4], const int64_t q_stride3[3
 template <int DT, int BITS, int MODE>
 void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const RowGeom& g, float eps, void* q,
                         void* scale_out, float* scale_f32_out, uint32_t* absmax_out, int accumulate,
-                        const TokBatch& tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}) {
-#define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
+                        const TokBatch& tb = TokBatch{nullptr, nullptr, nullptr, nullptr, 0}, const Publish& xc = Publish()) {
+#define KVQ_TF(NV) token_fused_kernel<DT, BITS, NV, MODE><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb, xc)
 #define KVQ_TFT(TPT) token_fused_kernel<DT, BITS, 8, MODE, TPT><<<dim3((unsigned)tgrid, grid.y), kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb)
     // small tokens, many of them: several tokens per CTA, TPT threads each (eight vectors per thread)
-    if (MODE == 0 && nv >= 1 && (int64_t)g.nP * g.vpr <= KVQ_TOKEN_TPT_MAX_VEC && g.T >= 1024) {
+    if (MODE == 0 && !xc.peers && nv >= 1 && (int64_t)g.nP * g.vpr <= KVQ_TOKEN_TPT_MAX_VEC && g.T >= 1024) {
         const int64_t n_vec = (int64_t)g.nP * g.vpr;
         const int tpt = n_vec <= 8 * 32 ? 32 : n_vec <= 8 * 64 ? 64 : 128;
         const int64_t groups = (g.T + (kThreads / tpt) - 1) / (kThreads / tpt);
@@ -1156,9 +1184,9 @@ extern "C" int kvq_quant_int4_pack(const void* x, int dtype, const int64_t shape
                            scale_f32_out, (cudaStream_t)stream);
 }
 
-extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
-                                         int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
-                                         float* scale_f32_out, uint32_t* absmax_bits_out, kvq_stream_t stream) {
+static int run_token_fused(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
+                           int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
+                           float* scale_f32_out, uint32_t* absmax_bits_out, const Publish& xc, kvq_stream_t stream) {
     KVQ_REQUIRE(x && q && shape && stride, "null pointer");
     KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4, got %d", bits);
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
@@ -1177,15 +1205,22 @@ extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t
         int nv = (int)((n_vec + kThreads - 1) / kThreads);
         const int64_t xmax = ((v.B - 1) * v.sB + (v.H - 1) * v.sH + v.D) * es, qmaxo = (v.B - 1) * qs.sB + (v.H - 1) * qs.sH + W;
         if (xmax >= 0xffffffffLL || qmaxo >= 0xffffffffLL || xmax < 0 || qmaxo < 0) nv = 9;  // offsets need 64 bits: two-loop variant
+        dim3 grid = token_grid(v.T);
+        if (xc.peers) {
+            KVQ_REQUIRE(v.T <= kXchMaxWords, "quant_per_token_fused_exchange: at most %d tokens per call (got %lld)", kXchMaxWords, (long long)v.T);
+            grid = dim3((unsigned)v.T);   // one CTA per token: every token of the call is published without waiting for a slot of this grid
+        }
+        const TokBatch none{nullptr, nullptr, nullptr, nullptr, 0};
         if (bits == 8) {
-            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, token_grid(v.T), st, x, g, eps, q, scale_out,
-                                                                scale_f32_out, absmax_bits_out, 0));
+            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, grid, st, x, g, eps, q, scale_out, scale_f32_out, absmax_bits_out, 0, none, xc));
         } else {
-            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, token_grid(v.T), st, x, g, eps, q, scale_out,
-                                                                scale_f32_out, absmax_bits_out, 0));
+            KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, grid, st, x, g, eps, q, scale_out, scale_f32_out, absmax_bits_out, 0, none, xc));
         }
         return check_launch("quant_per_token_fused");
     }
+    if (xc.peers)
+        return fail(KVQ_ERR_UNSUPPORTED, "quant_per_token_fused_exchange: needs the default eps and rows of 16-byte multiples with 16-byte-aligned "
+                                         "strides (take the allreduce form for other layouts)");
     // generic shapes: two generic phases through a caller-provided absmax buffer
     KVQ_REQUIRE(absmax_bits_out != nullptr,
                 "quant_per_token_fused: this shape/stride needs the generic path, which requires absmax_bits_out");
@@ -1198,10 +1233,44 @@ extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t
                            scale_f32_out, st);
 }
 
-extern "C" int kvq_quant_per_token_fused_batched(const void* const* xs, int dtype, int64_t n_tensors, const int64_t shape[4],
-                                                 const int64_t stride[4], int bits, float eps, void* const* qs,
-                                                 const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
-                                                 float* const* scales_f32_out, kvq_stream_t stream) {
+extern "C" int kvq_quant_per_token_fused(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
+                                         int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
+                                         float* scale_f32_out, uint32_t* absmax_bits_out, kvq_stream_t stream) {
+    return run_token_fused(x, dtype, shape, stride, bits, eps, q, q_stride3, scale_out, scale_f32_out, absmax_bits_out, Publish(), stream);
+}
+
+static int check_exchange_args(void* const* peer_buffers, int rank, int world_size, uint32_t seq, int64_t n_tensors) {
+    KVQ_REQUIRE(peer_buffers, "null pointer");
+    KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld && rank >= 0 && rank < world_size, "bad rank / world size");
+    KVQ_REQUIRE(n_tensors <= kXchMaxWords, "publish / gather: at most %d tensors per call (got %lld)", kXchMaxWords, (long long)n_tensors);
+    KVQ_REQUIRE(seq != 0, "seq must be a non-zero step counter, the same on every rank (buffers start zeroed)");
+    return KVQ_OK;
+}
+
+// The step counter of the exchange forms is a LAUNCH ARGUMENT: a captured graph would replay the same number and accept the previous
+// replay's words.  Refuse instead (the caller falls back to the NCCL allreduce, which is capturable).
+static int not_capturing(kvq_stream_t stream, const char* what) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    KVQ_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) return fail(KVQ_ERR_UNSUPPORTED, "%s: not capturable into a CUDA graph (the step counter is a launch argument)", what);
+    return KVQ_OK;
+}
+
+extern "C" int kvq_quant_per_token_fused_exchange(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
+                                                  int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
+                                                  float* scale_f32_out, uint32_t* absmax_bits_out, void* const* peer_buffers, int rank,
+                                                  int world_size, uint32_t seq, kvq_stream_t stream) {
+    if (int rc = check_exchange_args(peer_buffers, rank, world_size, seq, 0)) return rc;
+    if (int rc = not_capturing(stream, "quant_per_token_fused_exchange")) return rc;
+    KVQ_REQUIRE(shape && shape[0] * shape[1] * shape[2] * shape[3] != 0, "exchange: an empty input publishes nothing (every rank must publish every call)");
+    Publish xc; xc.peers = peer_buffers; xc.rank = rank; xc.world = world_size; xc.seq = seq;
+    return run_token_fused(x, dtype, shape, stride, bits, eps, q, q_stride3, scale_out, scale_f32_out, absmax_bits_out, xc, stream);
+}
+
+static int run_token_fused_batched(const void* const* xs, int dtype, int64_t n_tensors, const int64_t shape[4],
+                                   const int64_t stride[4], int bits, float eps, void* const* qs,
+                                   const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
+                                   float* const* scales_f32_out, const Publish& xc, kvq_stream_t stream) {
     KVQ_REQUIRE(xs && qs && shape && stride, "null pointer");
     KVQ_REQUIRE(bits == 8 || bits == 4, "bits must be 8 or 4, got %d", bits);
     KVQ_REQUIRE(dtype >= 0 && dtype <= 2, "unknown dtype %d", dtype);
@@ -1232,12 +1301,21 @@ extern "C" int kvq_quant_per_token_fused_batched(const void* const* xs, int dtyp
     if (gx < 1) gx = 1;
     const dim3 grid((unsigned)gx, (unsigned)n_tensors);
     if (bits == 8) {
-        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb));
+        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 8, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb, xc));
     } else {
-        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb));
+        KVQ_DISPATCH_DT(dtype, launch_token_fused<DT, 4, 0>(nv, grid, st, nullptr, g, eps, nullptr, nullptr, nullptr, nullptr, 0, tb, xc));
     }
     return check_launch("quant_per_token_fused_batched");
 }
+
+extern "C" int kvq_quant_per_token_fused_batched(const void* const* xs, int dtype, int64_t n_tensors, const int64_t shape[4],
+                                                 const int64_t stride[4], int bits, float eps, void* const* qs,
+                                                 const int64_t q_stride3[3], int64_t dst_token_offset, void* const* scales_out,
+                                                 float* const* scales_f32_out, kvq_stream_t stream) {
+    return run_token_fused_batched(xs, dtype, n_tensors, shape, stride, bits, eps, qs, q_stride3, dst_token_offset, scales_out, scales_f32_out,
+                                   Publish(), stream);
+}
+
 
 extern "C" int kvq_dequant_int8(const int8_t* q, const int64_t shape[4], const int64_t q_stride3[3], const void* scale,
                                 int scale_dtype, int granularity, void* out, int out_dtype, kvq_stream_t stream) {
@@ -1254,14 +1332,6 @@ extern "C" int kvq_dequant_int4_unpack(const uint8_t* packed, const int64_t shap
 // One launch per phase for a whole step (all layers x {K,V}) instead of one per tensor: at 1/8 of a cache per GPU the
 // per-tensor kernels last 20-30 us and launch gaps dominate.  Pointer tables live on the device.
 
-
-static int check_exchange_args(void* const* peer_buffers, int rank, int world_size, uint32_t seq, int64_t n_tensors) {
-    KVQ_REQUIRE(peer_buffers, "null pointer");
-    KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld && rank >= 0 && rank < world_size, "bad rank / world size");
-    KVQ_REQUIRE(n_tensors <= kXchMaxWords, "publish / gather: at most %d tensors per call (got %lld)", kXchMaxWords, (long long)n_tensors);
-    KVQ_REQUIRE(seq != 0, "seq must be a non-zero step counter, the same on every rank (buffers start zeroed)");
-    return KVQ_OK;
-}
 
 static int run_absmax_batched(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits, Publish pub,
                               kvq_stream_t stream) {
@@ -1290,6 +1360,7 @@ extern "C" int kvq_absmax_batched(const void* const* xs, int dtype, int64_t n_te
 extern "C" int kvq_absmax_batched_publish(const void* const* xs, int dtype, int64_t n_tensors, int64_t numel, uint32_t* absmax_bits,
                                           void* const* peer_buffers, int rank, int world_size, uint32_t seq, kvq_stream_t stream) {
     if (int rc = check_exchange_args(peer_buffers, rank, world_size, seq, n_tensors)) return rc;
+    if (int rc = not_capturing(stream, "absmax_batched_publish")) return rc;
     KVQ_REQUIRE(numel > 0 || n_tensors == 0, "publish: empty tensors publish nothing (every rank must publish every step)");
     Publish pub; pub.peers = peer_buffers; pub.rank = rank; pub.world = world_size; pub.seq = seq;
     return run_absmax_batched(xs, dtype, n_tensors, numel, absmax_bits, pub, stream);
@@ -1333,6 +1404,7 @@ extern "C" int kvq_quant_batched_gather(const void* const* xs, int dtype, int64_
     KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld, "bad world size");
     KVQ_REQUIRE(n_tensors <= kXchMaxWords, "publish / gather: at most %d tensors per call (got %lld)", kXchMaxWords, (long long)n_tensors);
     KVQ_REQUIRE(seq != 0, "seq must be the step counter given to kvq_absmax_batched_publish");
+    if (int rc = not_capturing(stream, "quant_batched_gather")) return rc;
     Gather gat; gat.mine = local_buffer; gat.world = world_size; gat.seq = seq;
     return run_quant_batched(xs, dtype, n_tensors, numel, bits, nullptr, eps, qs, scale_out, scale_f32_out, gat, absmax_bits_out, stream);
 }

@@ -69,6 +69,10 @@ extern "C" int kvq_absmax_exchange(uint32_t* absmax_bits, int64_t n_words, void*
     KVQ_REQUIRE(n_words >= 1 && n_words <= kXchMaxWords, "absmax_exchange: 1 .. %d words per call (got %lld)", kXchMaxWords, (long long)n_words);
     KVQ_REQUIRE(world_size >= 1 && world_size <= kXchMaxWorld && rank >= 0 && rank < world_size, "bad rank / world size");
     KVQ_REQUIRE(seq != 0, "seq must be a non-zero, increasing step counter (buffers start zeroed)");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    KVQ_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone)  // a replayed graph would present the same step number again and accept stale words
+        return fail(KVQ_ERR_UNSUPPORTED, "absmax_exchange: not capturable into a CUDA graph (the step counter is a launch argument)");
     absmax_exchange_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(absmax_bits, (int)n_words, reinterpret_cast<uint32_t* const*>(peer_buffers), rank,
                                                                world_size, seq);
     return check_launch("absmax_exchange");

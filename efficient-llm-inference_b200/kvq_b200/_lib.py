@@ -59,6 +59,8 @@ SIGNATURES = {
     "kvq_quant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp]),
     "kvq_dequant_batched": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
     "kvq_quant_per_token_fused_batched": (c_int, [c_vp, c_int, c_i64, I64x4, I64x4, c_int, c_f, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "kvq_quant_per_token_fused_exchange": (c_int, [c_vp, c_int, I64x4, I64x4, c_int, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int,
+                                                   ctypes.c_uint32, c_vp]),
     "kvq_evict_gather_batched": (c_int, [c_vp, c_vp, c_i64, c_int, I64x4, I64x4, ctypes.POINTER(EvictPlan), c_vp, c_vp, c_vp]),
     "kvq_evict_old_table_device": (c_int, [ctypes.POINTER(EvictPlan), c_vp, c_vp]),
     "kvq_chunk_mean_batched": (c_int, [c_vp, c_vp, c_i64, c_int, I64x4, I64x4, c_i64, c_i64, c_vp]),

@@ -119,3 +119,17 @@ class AbsmaxExchange:
     @property
     def local_buffer_ptr(self) -> int:
         return self._local
+
+
+_SHARED = {}
+
+
+def shared_exchange(device: torch.device, group=None) -> Optional["AbsmaxExchange"]:
+    """One AbsmaxExchange per (device, group) for every layer store of a head-sharded cache: one buffer, one step counter (all
+    ranks issue the same calls in the same order).  Created on first use -- a collective: every rank of `group` must get here.
+    None when symmetric memory is unavailable (the callers then use the NCCL allreduce)."""
+    key = (torch.device(device).index, None if group is None or group is True else id(group))
+    ex = _SHARED.get(key)
+    if ex is None:
+        ex = _SHARED[key] = AbsmaxExchange(torch.device(device), None if group is True else group)
+    return ex if ex.available else None

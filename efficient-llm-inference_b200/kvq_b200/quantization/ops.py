@@ -356,6 +356,34 @@ class _TokenStore:
             st_.n_scale_entries += n
         return True
 
+    def append_per_token_exchange(self, x: torch.Tensor, exchange, eps: float = 1e-8) -> bool:
+        """Head-sharded append_per_token in ONE launch, the max over ranks taken INSIDE the kernel through peer-mapped memory
+        (kvq_quant_per_token_fused_exchange) -- instead of absmax kernel + NCCL allreduce + quantize kernel.  Returns False --
+        nothing appended -- when the layout / size / capture state does not allow it; the caller then takes the allreduce path.
+        Every rank must make the same calls in the same order."""
+        n = x.size(2)
+        if exchange is None or float(eps) != 1e-8 or n > 1024 or x.stride(3) != 1 or (x.size(3) * x.element_size()) % 16:
+            return False
+        if torch.cuda.is_current_stream_capturing():   # the step counter is a launch argument: a replay would reuse it
+            return False
+        self._reserve(x, n)
+        lo = self.start + self.T
+        sh, st = L.shape_stride(x)
+        codes = self.codes
+        if self._stride3_of is not codes:
+            self._stride3, self._stride3_of = L.stride3(codes), codes
+        rc = L.lib().kvq_quant_per_token_fused_exchange(
+            x.data_ptr(), L.dtype_code(x.dtype), sh, st, self.bits, float(eps), codes.data_ptr() + lo * codes.stride(2), self._stride3,
+            self.scales.data_ptr() + lo * self.scales.element_size(), self.scales_f32.data_ptr() + 4 * lo, None,
+            exchange.peer_table_ptr, exchange.rank, exchange.world, exchange.next_fused_seq(), L.stream_ptr(x.device))
+        if rc == L.KVQ_ERR_UNSUPPORTED:   # layout (every rank sees the same one), or a capture in progress
+            return False
+        L.check(rc, "kvq_quant_per_token_fused_exchange")
+        L.count_launch()
+        self.T += n
+        self.n_scale_entries += n
+        return True
+
     def append_shared_scale(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
         """The reference's append() given n > 1 tokens: ONE scale over the whole [B,H,n,D] block
         (ops.py:181-210 calls the per-tensor helper on whatever it is handed)."""
@@ -485,6 +513,9 @@ class QuantizedLayerKV:
         """Append one token's K and V, each [B,H,1,D], quantized with its own scale."""
         self._check_pair(k_1tok, v_1tok)
         with L.device_guard(k_1tok):
+            if k_1tok.size(2) == 1 and v_1tok.size(2) == 1:
+                self._append_per_token_pair(k_1tok, v_1tok)
+                return
             for store, x in ((self._k, k_1tok), (self._v, v_1tok)):
                 if x.size(2) == 1:
                     store.append_per_token(x, group=self.group)
@@ -497,8 +528,21 @@ class QuantizedLayerKV:
         token each (what init_from_prompt_past does, ops.py:339-342), in one launch per tensor."""
         self._check_pair(k, v)
         with L.device_guard(k):
-            self._k.append_per_token(k, group=self.group)
-            self._v.append_per_token(v, group=self.group)
+            self._append_per_token_pair(k, v)
+
+    def _append_per_token_pair(self, k: torch.Tensor, v: torch.Tensor) -> None:
+        if self.group is not None:
+            # head-sharded: the max over ranks inside the quantize kernel (one launch per tensor); the NCCL allreduce form when
+            # peer-mapped memory is not available or the step is being captured
+            from ..distributed import shared_exchange
+            ex = shared_exchange(k.device, self.group)
+            if ex is not None:
+                for store, x in ((self._k, k), (self._v, v)):
+                    if not store.append_per_token_exchange(x, ex):
+                        store.append_per_token(x, group=self.group)
+                return
+        self._k.append_per_token(k, group=self.group)
+        self._v.append_per_token(v, group=self.group)
 
     @torch.no_grad()
     def get_kv(self) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -194,6 +194,20 @@ KVQ_API int kvq_quant_batched_gather(const void* const* xs, int dtype, int64_t n
                                      uint32_t* absmax_bits_out, float eps, void* const* qs, void* scale_out, float* scale_f32_out,
                                      void* local_buffer, int world_size, uint32_t seq, kvq_stream_t stream);
 
+/* The per-token append of a head-sharded cache in ONE kernel: kvq_quant_per_token_fused whose CTAs, between the token's on-chip
+ * max and the quantization of the values they hold in registers, store the token's word (tagged with `seq`) into every rank's
+ * buffer and wait for the world's words of the same token.  What a decode step appends (one token of K, one of V per layer)
+ * costs one launch per tensor instead of absmax kernel + allreduce + quantize kernel.  At most 1024 tokens per call; every rank
+ * calls it with the same token count and `seq`, in the same order, on one stream.  absmax_bits_out (nullable) receives the
+ * combined words.  Scales and codes are bit-identical to the allreduce form (ops.py:330,:342 with the scale over all heads).
+ * KVQ_ERR_UNSUPPORTED for layouts the vector path cannot take (custom eps, rows that are not 16-byte multiples), and -- like
+ * every entry point that takes `seq` -- while the stream is being captured into a CUDA graph (a replay would present the same
+ * step number again). */
+KVQ_API int kvq_quant_per_token_fused_exchange(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
+                                               int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
+                                               float* scale_f32_out, uint32_t* absmax_bits_out, void* const* peer_buffers, int rank,
+                                               int world_size, uint32_t seq, kvq_stream_t stream);
+
 /* ---------------------------------------------------------------------------------- area 2: eviction
  * The kept index set is a closed form of (T, parameters): the gather kernel computes the source token
  * of every destination row in registers; no index tensor and no intermediate parts list exists. */

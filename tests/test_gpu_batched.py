@@ -178,3 +178,108 @@ def test_small_tokens_several_per_cta(kvq, oracle, dtype, shape):
         oq, osc, _ = oracle.quantize_per_token(x, bits)
         assert torch.equal(kc.cpu(), oq) and torch.equal(vc.cpu(), oq)
         assert torch.equal(ks.cpu(), osc.float()) and torch.equal(vs.cpu(), osc.float())
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_publish_gather_on_one_device_equals_the_plain_batched_pair(kvq, bits, world):
+    """kvq_absmax_batched_publish / kvq_quant_batched_gather (the head-sharded pair with the exchange inside the kernels) with
+    all `world` ranks played by ONE device: every rank publishes into every rank's buffer, then every rank gathers.  Codes and
+    scales of every shard equal the single-GPU batched quantization of the full tensors, for several steps in a row (slot
+    parity, arrival counters re-armed, the max moving between ranks).  Reference: scale over all heads, ops.py:27,:48."""
+    from kvq_b200 import _lib as L
+    from kvq_b200.quantization.ops import TensorTable, quantize_per_tensor_batched
+    lib, dev = L.lib(), torch.device("cuda")
+    nbytes = int(lib.kvq_absmax_exchange_buffer_bytes())
+    bufs = [torch.zeros(nbytes // 4, dtype=torch.int32, device=dev) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64).to(dev)
+    B, H, T, D, nt = 2, 2 * world, 2048, 64, 3       # 2048 * 64 * 2 heads * 2 B * 2 = 1 MiB per shard: many CTAs per tensor
+    W = D if bits == 8 else D // 2
+    cdt = torch.int8 if bits == 8 else torch.uint8
+    stream = L.stream_ptr(dev)
+    for step in range(1, 6):
+        g = torch.Generator(device="cuda").manual_seed(100 * step + world)
+        fulls = [(torch.randn(B, H, T, D, device=dev, generator=g) * (i + step)).to(torch.bfloat16) for i in range(nt)]
+        fulls[step % nt][1, (3 * step) % H, 17, 5] = 500.0 + step
+        fq = [torch.empty(B, H, T, W, device=dev, dtype=cdt) for _ in range(nt)]
+        fs = torch.empty(nt, device=dev, dtype=torch.bfloat16)
+        fb = quantize_per_tensor_batched(TensorTable(fulls), TensorTable(fq), bits, fs)
+        Hl = H // world
+        shards = [[f[:, r * Hl:(r + 1) * Hl].contiguous() for f in fulls] for r in range(world)]
+        tabs = [TensorTable(s) for s in shards]
+        local = [torch.empty(nt, dtype=torch.int32, device=dev) for _ in range(world)]
+        for r in range(world):
+            L.check(lib.kvq_absmax_batched_publish(tabs[r].ptrs.data_ptr(), L.BF16, nt, tabs[r].numel, local[r].data_ptr(), peers.data_ptr(),
+                                                   r, world, step, stream), "publish")
+        for r in range(world):
+            sq = [torch.empty(B, Hl, T, W, device=dev, dtype=cdt) for _ in range(nt)]
+            qt = TensorTable(sq)
+            ss = torch.empty(nt, device=dev, dtype=torch.bfloat16)
+            comb = torch.empty(nt, dtype=torch.int32, device=dev)
+            L.check(lib.kvq_quant_batched_gather(tabs[r].ptrs.data_ptr(), L.BF16, nt, tabs[r].numel, bits | L.ABSMAX_COVERS_INPUT, comb.data_ptr(),
+                                                 1e-8, qt.ptrs.data_ptr(), ss.data_ptr(), None, bufs[r].data_ptr(), world, step, stream), "gather")
+            assert torch.equal(comb, fb), (step, r)
+            assert torch.equal(ss.view(torch.int16), fs.view(torch.int16))
+            for a, f in zip(sq, fq):
+                assert torch.equal(a, f[:, r * Hl:(r + 1) * Hl])
+            # the local words are the shard's own absmax
+            want = torch.stack([s.abs().max().float() for s in shards[r]]).view(torch.int32)
+            assert torch.equal(local[r], want)
+
+
+def test_publish_gather_argument_checks(kvq):
+    from kvq_b200 import _lib as L
+    lib, dev = L.lib(), torch.device("cuda")
+    buf = torch.zeros(int(lib.kvq_absmax_exchange_buffer_bytes()) // 4, dtype=torch.int32, device=dev)
+    peers = torch.tensor([buf.data_ptr()], dtype=torch.int64).to(dev)
+    x = torch.zeros(1, 1, 8, 64, device=dev, dtype=torch.bfloat16)
+    xt = torch.tensor([x.data_ptr()], dtype=torch.int64).to(dev)
+    bits = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = L.stream_ptr(dev)
+    assert lib.kvq_absmax_batched_publish(xt.data_ptr(), L.BF16, 1, x.numel(), bits.data_ptr(), peers.data_ptr(), 0, 1, 0, st) == -1   # seq 0
+    assert lib.kvq_absmax_batched_publish(xt.data_ptr(), L.BF16, 1, x.numel(), bits.data_ptr(), peers.data_ptr(), 1, 1, 1, st) == -1   # rank >= world
+    assert lib.kvq_absmax_batched_publish(xt.data_ptr(), L.BF16, 2000, x.numel(), bits.data_ptr(), peers.data_ptr(), 0, 1, 1, st) == -1  # too many tensors
+    assert lib.kvq_absmax_batched_publish(xt.data_ptr(), L.BF16, 1, x.numel(), bits.data_ptr(), None, 0, 1, 1, st) == -1
+    q = torch.empty(1, 1, 8, 64, device=dev, dtype=torch.int8)
+    qt = torch.tensor([q.data_ptr()], dtype=torch.int64).to(dev)
+    sc = torch.empty(1, device=dev, dtype=torch.bfloat16)
+    assert lib.kvq_quant_batched_gather(xt.data_ptr(), L.BF16, 1, x.numel(), 8, bits.data_ptr(), 1e-8, qt.data_ptr(), sc.data_ptr(), None, None, 1, 1, st) == -1
+    assert lib.kvq_quant_batched_gather(xt.data_ptr(), L.BF16, 1, x.numel(), 8, bits.data_ptr(), 1e-8, qt.data_ptr(), sc.data_ptr(), None, buf.data_ptr(), 1, 0, st) == -1
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("shape", [(8, 2, 1, 128), (2, 3, 37, 64), (1, 1, 5, 8)])
+def test_per_token_exchange_with_one_rank_equals_the_plain_fused_quantizer(kvq, bits, shape):
+    """kvq_quant_per_token_fused_exchange with world = 1 (the rank's own buffer is the only peer): same codes, scales and absmax
+    words as kvq_quant_per_token_fused, call after call (slot parity / step tags).  The 2-GPU form is in test_gpu_multi.py."""
+    from kvq_b200 import _lib as L
+    lib, dev = L.lib(), torch.device("cuda")
+    buf = torch.zeros(int(lib.kvq_absmax_exchange_buffer_bytes()) // 4, dtype=torch.int32, device=dev)
+    peers = torch.tensor([buf.data_ptr()], dtype=torch.int64).to(dev)
+    B, H, T, D = shape
+    W = D if bits == 8 else D // 2
+    st = L.stream_ptr(dev)
+    for step in range(1, 5):
+        x = (gen(shape, torch.bfloat16, 50 + step) * step).to(dev)
+        outs = []
+        for form in ("plain", "exchange"):
+            q = torch.zeros(B, H, T, W, device=dev, dtype=torch.uint8)
+            sc = torch.zeros(T, device=dev, dtype=torch.bfloat16)
+            s32 = torch.zeros(T, device=dev, dtype=torch.float32)
+            am = torch.zeros(T, device=dev, dtype=torch.int32)
+            sh, sx = L.shape_stride(x)
+            if form == "plain":
+                L.check(lib.kvq_quant_per_token_fused(x.data_ptr(), L.BF16, sh, sx, bits, 1e-8, q.data_ptr(), L.stride3(q), sc.data_ptr(), s32.data_ptr(),
+                                                      am.data_ptr(), st), "plain")
+            else:
+                L.check(lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, bits, 1e-8, q.data_ptr(), L.stride3(q), sc.data_ptr(),
+                                                               s32.data_ptr(), am.data_ptr(), peers.data_ptr(), 0, 1, step, st), "exchange")
+            outs.append((q, sc, s32, am))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+    # argument checks: step 0, too many tokens, a custom eps (exact-division path: not in the single-pass kernel)
+    x = gen((1, 1, 4, 64), torch.bfloat16, 1).to(dev)
+    q = torch.zeros(1, 1, 4, 64, device=dev, dtype=torch.uint8)
+    sh, sx = L.shape_stride(x)
+    assert lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, 8, 1e-8, q.data_ptr(), L.stride3(q), None, None, None, peers.data_ptr(), 0, 1, 0, st) == -1
+    assert lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, 8, 1e-3, q.data_ptr(), L.stride3(q), None, None, None, peers.data_ptr(), 0, 1, 9, st) == -3

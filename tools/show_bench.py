@@ -11,6 +11,7 @@ for leg in ("per_token", "c4", "paged"):
 if r.get("decode"):
     for k, v in r["decode"].items():
         if isinstance(v, dict) and "tok_s" in v: print("decode", k, round(v["tok_s"], 1), "tok/s", round(v["ms_per_step"], 2), "ms", rf(v["roofline"]))
+        if k == "append_sharded": print("decode append (head-sharded)", v)
 for leg in ("c2", "c1"):
     if r.get(leg):
         for k, v in r[leg].items():
