@@ -66,8 +66,9 @@ class _PagedStream:
 
     def append_per_token(self, x: torch.Tensor, eps: float = 1e-8, group=None) -> None:
         """n tokens, one scale each, quantized straight into their blocks: one launch per block touched.  `group`: the store
-        holds a head shard; the per-token absmax is all-reduced (MAX) over the group between the two phases, so codes and
-        scales equal the unsharded store's, bit for bit."""
+        holds a head shard; the per-token absmax is max-combined over the group -- inside the quantize kernel through peer-mapped
+        memory (kvq_quant_per_token_fused_exchange), or absmax -> NCCL allreduce(MAX) -> quantize where that is unavailable --
+        so codes and scales equal the unsharded store's, bit for bit."""
         B, H, n, D = x.shape
         if self.codes is not None and (tuple(self.codes.shape[1:3]) != (B, H) or self.D != D or self.scales.dtype != x.dtype):
             raise RuntimeError("appended tensor does not match the cache")
@@ -86,6 +87,10 @@ class _PagedStream:
         if bits is None or bits.numel() < min(n, self.bs) or bits.device != x.device:
             bits = self._bits_scratch = torch.empty(max(self.bs, 64), dtype=torch.int32, device=x.device)
         es = self.scales.element_size()
+        ex = None
+        if group is not None and float(eps) == 1e-8 and not torch.cuda.is_current_stream_capturing():
+            from ..distributed import shared_exchange
+            ex = shared_exchange(x.device, group)   # None: no peer-mapped memory on this node -> the allreduce form
         done = 0
         while done < n:  # destination pointers by arithmetic on the pools: the decode loop comes through here every step
             t = self.T + done
@@ -101,15 +106,26 @@ class _PagedStream:
                                                       self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
                                                       bits.data_ptr(), stream), "kvq_quant_per_token_fused")
                 L.count_launch()
-            else:  # head shard: absmax of the shard -> allreduce(MAX) -> quantize with the global per-token scale
-                from ..distributed import allreduce_absmax_
-                gb = torch.empty(m, dtype=torch.int32, device=x.device)
-                L.check(lib.kvq_absmax(src.data_ptr(), dt, sh, st, L.PER_TOKEN, gb.data_ptr(), 0, stream), "kvq_absmax")
-                allreduce_absmax_(gb, group)
-                fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
-                L.check(fn(src.data_ptr(), dt, sh, st, L.PER_TOKEN | L.ABSMAX_COVERS_INPUT, gb.data_ptr(), float(eps), dst, self._stride3,
-                           self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot, stream), "kvq_quant (per token)")
-                L.count_launch(2)
+                done += m
+                continue
+            if ex is not None:  # head shard, one launch: the max over ranks inside the quantize kernel (peer-mapped memory)
+                rc = lib.kvq_quant_per_token_fused_exchange(src.data_ptr(), dt, sh, st, self.bits, float(eps), dst, self._stride3,
+                                                            self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
+                                                            None, ex.peer_table_ptr, ex.rank, ex.world, ex.next_fused_seq(), stream)
+                if rc != L.KVQ_ERR_UNSUPPORTED:   # (unsupported layout: the same on every rank -> all take the form below)
+                    L.check(rc, "kvq_quant_per_token_fused_exchange")
+                    L.count_launch()
+                    done += m
+                    continue
+            # head shard, fallback: absmax of the shard -> allreduce(MAX) -> quantize with the global per-token scale
+            from ..distributed import allreduce_absmax_
+            gb = torch.empty(m, dtype=torch.int32, device=x.device)
+            L.check(lib.kvq_absmax(src.data_ptr(), dt, sh, st, L.PER_TOKEN, gb.data_ptr(), 0, stream), "kvq_absmax")
+            allreduce_absmax_(gb, group)
+            fn = lib.kvq_quant_int8 if self.bits == 8 else lib.kvq_quant_int4_pack
+            L.check(fn(src.data_ptr(), dt, sh, st, L.PER_TOKEN | L.ABSMAX_COVERS_INPUT, gb.data_ptr(), float(eps), dst, self._stride3,
+                       self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot, stream), "kvq_quant (per token)")
+            L.count_launch(2)
             done += m
         self.T += n
 
