@@ -918,6 +918,30 @@ def run_append_sharded(cx: Ctx, B, Hl, D, Lyr):
         res[name + "_launches_per_step"] = (L.launch_count - l0) // n
         for l in layers:
             l._k.keep_last(64), l._v.keep_last(64)
+    if have_x:
+        # the exchange form takes its step number from the device, so the whole 80-layer append can sit in a CUDA graph (as a serving
+        # loop would capture it): device time without the host's 12 us per call
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            graph.capture_begin()
+            step_exchange()
+            graph.capture_end()
+        torch.cuda.synchronize()
+        for _ in range(3):
+            graph.replay()
+        cx.sync_all()
+        n = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            graph.replay()
+        e1.record()
+        cx.sync_all()
+        cx.launches += 2 * Lyr * (n + 4)
+        res["exchange_cuda_graph_ms_per_step"] = cx.max_over_ranks(e0.elapsed_time(e1) / n)
+        del graph
     return res
 
 

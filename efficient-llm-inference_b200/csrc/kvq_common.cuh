@@ -192,16 +192,25 @@ template <int THREADS> __device__ __forceinline__ uint32_t block_max_u32(uint32_
 //   uint32 flags  [2][kXchMaxWorld]                 ... and one sequence flag per (parity, source rank)
 //   uint64 tagged [2][kXchMaxWorld][kXchMaxWords]   publish / gather: (seq << 32 | word), ONE 8-byte store per word, no flag
 //   uint32 arrive [kXchMaxWords]                    local last-CTA counters of the publishing absmax kernel
+//   uint64 tagged2[2][kXchMaxWorld][kXchMaxWords]   the same as `tagged` for calls that take their step number from the DEVICE
+//   uint32 step   [4]                               counter below (seq == 0: capturable into CUDA graphs): [0] = steps completed,
+//                                                   [1] = CTA arrivals of the running kernel
 constexpr int kXchMaxWords = 1024;   // words per rank per parity
 constexpr int kXchMaxWorld = 16;
 __host__ __device__ inline size_t xch_word_off(int parity, int src_rank, int i) { return ((size_t)parity * kXchMaxWorld + src_rank) * kXchMaxWords + i; }
 __host__ __device__ inline size_t xch_flag_off(int parity, int src_rank) { return (size_t)2 * kXchMaxWorld * kXchMaxWords + (size_t)parity * kXchMaxWorld + src_rank; }
 constexpr size_t kXchTaggedByteOff = (size_t)(2 * kXchMaxWorld * kXchMaxWords + 2 * kXchMaxWorld) * 4;   // multiple of 8
 constexpr size_t kXchArriveByteOff = kXchTaggedByteOff + (size_t)2 * kXchMaxWorld * kXchMaxWords * 8;
-constexpr size_t kXchBufferBytes = kXchArriveByteOff + (size_t)kXchMaxWords * 4;
+constexpr size_t kXchTagged2ByteOff = kXchArriveByteOff + (size_t)kXchMaxWords * 4;   // multiple of 8
+constexpr size_t kXchStepByteOff = kXchTagged2ByteOff + (size_t)2 * kXchMaxWorld * kXchMaxWords * 8;
+constexpr size_t kXchBufferBytes = kXchStepByteOff + 16;
 __host__ __device__ inline unsigned long long* xch_tagged(void* buf, int parity, int src_rank, int i) {
     return reinterpret_cast<unsigned long long*>(static_cast<char*>(buf) + kXchTaggedByteOff) + xch_word_off(parity, src_rank, i);
 }
+__host__ __device__ inline unsigned long long* xch_tagged2(void* buf, int parity, int src_rank, int i) {
+    return reinterpret_cast<unsigned long long*>(static_cast<char*>(buf) + kXchTagged2ByteOff) + xch_word_off(parity, src_rank, i);
+}
+__host__ __device__ inline uint32_t* xch_step(void* buf) { return reinterpret_cast<uint32_t*>(static_cast<char*>(buf) + kXchStepByteOff); }
 __host__ __device__ inline uint32_t* xch_arrive(void* buf) { return reinterpret_cast<uint32_t*>(static_cast<char*>(buf) + kXchArriveByteOff); }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

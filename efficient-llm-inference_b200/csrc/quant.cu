@@ -466,6 +466,10 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
             }
         }
     }
+    // step number of the exchange form: the caller's (seq != 0), or -- capturable into a CUDA graph -- one more than the steps this
+    // rank's buffer has completed; the last CTA to finish records the completion (all CTAs have read the counter by then)
+    uint32_t xseq = xc.seq;
+    if (TPT == kThreads && MODE == 0 && xc.peers && xseq == 0) xseq = *reinterpret_cast<volatile uint32_t*>(xch_step(xc.peers[xc.rank])) + 1u;
     for (int64_t t0 = (int64_t)blockIdx.x * TOKS; t0 < g.T; t0 += (int64_t)gridDim.x * TOKS) {
         const int64_t t = t0 + slot;
         const bool live = t < g.T;   // (always true for TPT == kThreads)
@@ -495,15 +499,19 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
                 // both sides walk the tokens in the same order, so the oldest unfinished token of any rank always has its peers'
                 // words published or about to be: no cycle.  The values stay in registers across the wait.
                 __shared__ uint32_t combined;
-                const int widx = (int)blockIdx.y * (int)g.T + (int)t, parity = (int)(xc.seq & 1u);
-                if ((int)threadIdx.x < xc.world)
-                    st_release_sys_u64(xch_tagged(xc.peers[threadIdx.x], parity, xc.rank, widx), ((unsigned long long)xc.seq << 32) | m);
+                const int widx = (int)blockIdx.y * (int)g.T + (int)t, parity = (int)(xseq & 1u);
+                if ((int)threadIdx.x < xc.world) {
+                    void* peer = xc.peers[threadIdx.x];
+                    st_release_sys_u64(xc.seq ? xch_tagged(peer, parity, xc.rank, widx) : xch_tagged2(peer, parity, xc.rank, widx),
+                                       ((unsigned long long)xseq << 32) | m);
+                }
                 if (threadIdx.x < 32) {
                     uint32_t w = 0;
                     if ((int)threadIdx.x < xc.world) {
-                        const unsigned long long* slot_p = xch_tagged(xc.peers[xc.rank], parity, (int)threadIdx.x, widx);
+                        void* mine = xc.peers[xc.rank];
+                        const unsigned long long* slot_p = xc.seq ? xch_tagged(mine, parity, (int)threadIdx.x, widx) : xch_tagged2(mine, parity, (int)threadIdx.x, widx);
                         unsigned long long tg, spins = 0;
-                        while ((uint32_t)((tg = ld_acquire_sys_u64(slot_p)) >> 32) != xc.seq) {
+                        while ((uint32_t)((tg = ld_acquire_sys_u64(slot_p)) >> 32) != xseq) {
                             if (++spins > (1ull << 24)) __trap();   // a peer that never arrives: fail instead of hanging the GPU
                             __nanosleep(spins < 64 ? 0 : 500);
                         }
@@ -548,6 +556,15 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
             }
         }
         if constexpr (TPT != 32) __syncthreads();  // `red` is reused by the next token
+    }
+    if (TPT == kThreads && MODE == 0 && xc.peers && xc.seq == 0 && threadIdx.x == 0) {
+        uint32_t* stp = xch_step(xc.peers[xc.rank]);
+        __threadfence();
+        if (atomicAdd(stp + 1, 1u) == gridDim.x * gridDim.y - 1u) {
+            stp[1] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(stp) = xseq;
+        }
     }
 }
 
@@ -1260,8 +1277,9 @@ extern "C" int kvq_quant_per_token_fused_exchange(const void* x, int dtype, cons
                                                   int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
                                                   float* scale_f32_out, uint32_t* absmax_bits_out, void* const* peer_buffers, int rank,
                                                   int world_size, uint32_t seq, kvq_stream_t stream) {
-    if (int rc = check_exchange_args(peer_buffers, rank, world_size, seq, 0)) return rc;
-    if (int rc = not_capturing(stream, "quant_per_token_fused_exchange")) return rc;
+    if (int rc = check_exchange_args(peer_buffers, rank, world_size, seq ? seq : 1u, 0)) return rc;
+    if (seq != 0)
+        if (int rc = not_capturing(stream, "quant_per_token_fused_exchange")) return rc;
     KVQ_REQUIRE(shape && shape[0] * shape[1] * shape[2] * shape[3] != 0, "exchange: an empty input publishes nothing (every rank must publish every call)");
     Publish xc; xc.peers = peer_buffers; xc.rank = rank; xc.world = world_size; xc.seq = seq;
     return run_token_fused(x, dtype, shape, stride, bits, eps, q, q_stride3, scale_out, scale_f32_out, absmax_bits_out, xc, stream);

@@ -88,7 +88,7 @@ class _PagedStream:
             bits = self._bits_scratch = torch.empty(max(self.bs, 64), dtype=torch.int32, device=x.device)
         es = self.scales.element_size()
         ex = None
-        if group is not None and float(eps) == 1e-8 and not torch.cuda.is_current_stream_capturing():
+        if group is not None and float(eps) == 1e-8:
             from ..distributed import shared_exchange
             ex = shared_exchange(x.device, group)   # None: no peer-mapped memory on this node -> the allreduce form
         done = 0
@@ -111,7 +111,7 @@ class _PagedStream:
             if ex is not None:  # head shard, one launch: the max over ranks inside the quantize kernel (peer-mapped memory)
                 rc = lib.kvq_quant_per_token_fused_exchange(src.data_ptr(), dt, sh, st, self.bits, float(eps), dst, self._stride3,
                                                             self.scales.data_ptr() + slot * es, self.scales_f32.data_ptr() + 4 * slot,
-                                                            None, ex.peer_table_ptr, ex.rank, ex.world, ex.next_fused_seq(), stream)
+                                                            None, ex.peer_table_ptr, ex.rank, ex.world, 0, stream)   # 0: device-resident step counter
                 if rc != L.KVQ_ERR_UNSUPPORTED:   # (unsupported layout: the same on every rank -> all take the form below)
                     L.check(rc, "kvq_quant_per_token_fused_exchange")
                     L.count_launch()

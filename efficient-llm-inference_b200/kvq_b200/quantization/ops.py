@@ -359,12 +359,11 @@ class _TokenStore:
     def append_per_token_exchange(self, x: torch.Tensor, exchange, eps: float = 1e-8) -> bool:
         """Head-sharded append_per_token in ONE launch, the max over ranks taken INSIDE the kernel through peer-mapped memory
         (kvq_quant_per_token_fused_exchange) -- instead of absmax kernel + NCCL allreduce + quantize kernel.  Returns False --
-        nothing appended -- when the layout / size / capture state does not allow it; the caller then takes the allreduce path.
+        nothing appended -- when the layout / size does not allow it; the caller then takes the allreduce path.  The step number
+        lives on the device (seq = 0), so a decode step that contains this call can be captured into a CUDA graph and replayed.
         Every rank must make the same calls in the same order."""
         n = x.size(2)
         if exchange is None or float(eps) != 1e-8 or n > 1024 or x.stride(3) != 1 or (x.size(3) * x.element_size()) % 16:
-            return False
-        if torch.cuda.is_current_stream_capturing():   # the step counter is a launch argument: a replay would reuse it
             return False
         self._reserve(x, n)
         lo = self.start + self.T
@@ -375,8 +374,8 @@ class _TokenStore:
         rc = L.lib().kvq_quant_per_token_fused_exchange(
             x.data_ptr(), L.dtype_code(x.dtype), sh, st, self.bits, float(eps), codes.data_ptr() + lo * codes.stride(2), self._stride3,
             self.scales.data_ptr() + lo * self.scales.element_size(), self.scales_f32.data_ptr() + 4 * lo, None,
-            exchange.peer_table_ptr, exchange.rank, exchange.world, exchange.next_fused_seq(), L.stream_ptr(x.device))
-        if rc == L.KVQ_ERR_UNSUPPORTED:   # layout (every rank sees the same one), or a capture in progress
+            exchange.peer_table_ptr, exchange.rank, exchange.world, 0, L.stream_ptr(x.device))   # 0: device-resident step counter (capturable)
+        if rc == L.KVQ_ERR_UNSUPPORTED:   # layout (every rank sees the same one)
             return False
         L.check(rc, "kvq_quant_per_token_fused_exchange")
         L.count_launch()

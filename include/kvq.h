@@ -200,9 +200,12 @@ KVQ_API int kvq_quant_batched_gather(const void* const* xs, int dtype, int64_t n
  * costs one launch per tensor instead of absmax kernel + allreduce + quantize kernel.  At most 1024 tokens per call; every rank
  * calls it with the same token count and `seq`, in the same order, on one stream.  absmax_bits_out (nullable) receives the
  * combined words.  Scales and codes are bit-identical to the allreduce form (ops.py:330,:342 with the scale over all heads).
- * KVQ_ERR_UNSUPPORTED for layouts the vector path cannot take (custom eps, rows that are not 16-byte multiples), and -- like
- * every entry point that takes `seq` -- while the stream is being captured into a CUDA graph (a replay would present the same
- * step number again). */
+ * seq == 0: the step number is taken from a counter in the rank's own buffer (steps completed + 1; the last CTA of the launch
+ * records the completion), so the call can be captured into a CUDA graph and replayed -- the form the cache stores use; such
+ * calls use their own region of the buffer, so they may be mixed with seq != 0 calls and with the publish / gather pair.
+ * KVQ_ERR_UNSUPPORTED for layouts the vector path cannot take (custom eps, rows that are not 16-byte multiples), and for
+ * seq != 0 -- like every entry point that takes a host step number -- while the stream is being captured into a CUDA graph
+ * (a replay would present the same number again). */
 KVQ_API int kvq_quant_per_token_fused_exchange(const void* x, int dtype, const int64_t shape[4], const int64_t stride[4],
                                                int bits, float eps, void* q, const int64_t q_stride3[3], void* scale_out,
                                                float* scale_f32_out, uint32_t* absmax_bits_out, void* const* peer_buffers, int rank,

@@ -262,7 +262,7 @@ def test_per_token_exchange_with_one_rank_equals_the_plain_fused_quantizer(kvq, 
     for step in range(1, 5):
         x = (gen(shape, torch.bfloat16, 50 + step) * step).to(dev)
         outs = []
-        for form in ("plain", "exchange"):
+        for form in ("plain", "exchange", "exchange_device_step"):
             q = torch.zeros(B, H, T, W, device=dev, dtype=torch.uint8)
             sc = torch.zeros(T, device=dev, dtype=torch.bfloat16)
             s32 = torch.zeros(T, device=dev, dtype=torch.float32)
@@ -271,15 +271,20 @@ def test_per_token_exchange_with_one_rank_equals_the_plain_fused_quantizer(kvq, 
             if form == "plain":
                 L.check(lib.kvq_quant_per_token_fused(x.data_ptr(), L.BF16, sh, sx, bits, 1e-8, q.data_ptr(), L.stride3(q), sc.data_ptr(), s32.data_ptr(),
                                                       am.data_ptr(), st), "plain")
-            else:
+            else:   # step number from the host, or (0) from the counter in the buffer
                 L.check(lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, bits, 1e-8, q.data_ptr(), L.stride3(q), sc.data_ptr(),
-                                                               s32.data_ptr(), am.data_ptr(), peers.data_ptr(), 0, 1, step, st), "exchange")
+                                                               s32.data_ptr(), am.data_ptr(), peers.data_ptr(), 0, 1, step if form == "exchange" else 0,
+                                                               st), "exchange")
             outs.append((q, sc, s32, am))
-        for a, b in zip(*outs):
-            assert torch.equal(a, b)
-    # argument checks: step 0, too many tokens, a custom eps (exact-division path: not in the single-pass kernel)
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b)
+        # the device counter: `step` completed calls, arrivals re-armed
+        stepw = buf.view(torch.uint8)[-16:].view(torch.int32)
+        assert stepw[0].item() == step and stepw[1].item() == 0
+    # argument checks: a bad rank, a custom eps (exact-division path: not in the single-pass kernel)
     x = gen((1, 1, 4, 64), torch.bfloat16, 1).to(dev)
     q = torch.zeros(1, 1, 4, 64, device=dev, dtype=torch.uint8)
     sh, sx = L.shape_stride(x)
-    assert lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, 8, 1e-8, q.data_ptr(), L.stride3(q), None, None, None, peers.data_ptr(), 0, 1, 0, st) == -1
+    assert lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, 8, 1e-8, q.data_ptr(), L.stride3(q), None, None, None, peers.data_ptr(), 1, 1, 3, st) == -1
     assert lib.kvq_quant_per_token_fused_exchange(x.data_ptr(), L.BF16, sh, sx, 8, 1e-3, q.data_ptr(), L.stride3(q), None, None, None, peers.data_ptr(), 0, 1, 9, st) == -3
