@@ -423,7 +423,7 @@ struct TokBatch {
 // TPT: threads per token.  256: one token per CTA at a time (block-wide max).  32 / 64 / 128: 8 / 4 / 2 tokens per CTA at a time,
 // each owned by TPT threads -- for small tokens (a head shard at N = 8 is 4 KB per token: one vector per thread and two block
 // barriers per 4 KB with TPT = 256; with TPT = 32 a warp owns the token, eight vectors per lane, and the max is a REDUX).
-template <int DT, int BITS, int NV, int MODE, int TPT = kThreads>
+template <int DT, int BITS, int NV, int MODE, int TPT = kThreads, bool XCH = false>
 __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __restrict__ x, RowGeom g, float eps,
                                                               char* __restrict__ q, void* __restrict__ scale_out,
                                                               float* __restrict__ scale_f32_out,
@@ -468,8 +468,13 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
     }
     // step number of the exchange form: the caller's (seq != 0), or -- capturable into a CUDA graph -- one more than the steps this
     // rank's buffer has completed; the last CTA to finish records the completion (all CTAs have read the counter by then)
-    uint32_t xseq = xc.seq;
-    if (TPT == kThreads && MODE == 0 && xc.peers && xseq == 0) xseq = *reinterpret_cast<volatile uint32_t*>(xch_step(xc.peers[xc.rank])) + 1u;
+    // (XCH is its own instantiation: the plain quantizer keeps its registers and schedule -- folding the exchange in as a run-time
+    // branch cost the C3-shape per-token leg 8 %)
+    uint32_t xseq = 0;
+    if constexpr (XCH) {
+        xseq = xc.seq;
+        if (xseq == 0) xseq = *reinterpret_cast<volatile uint32_t*>(xch_step(xc.peers[xc.rank])) + 1u;
+    }
     for (int64_t t0 = (int64_t)blockIdx.x * TOKS; t0 < g.T; t0 += (int64_t)gridDim.x * TOKS) {
         const int64_t t = t0 + slot;
         const bool live = t < g.T;   // (always true for TPT == kThreads)
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
         }
         if constexpr (TPT == kThreads) {
             m = block_max_u32<kThreads>(InVec<DT>::finish_absmax(m), red);
-            if (MODE == 0 && xc.peers) {
+            if constexpr (XCH) {
                 // head-sharded append in ONE kernel (kvq_quant_per_token_fused_exchange): the token's local word goes, tagged with
                 // the step number, into every rank's peer-mapped buffer; then the CTA waits for the world's words of this token
                 // and max-combines them -- the scale is over all heads (ops.py:330,:342).  Every CTA publishes before it waits and
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) token_fused_kernel(const char* __res
         }
         if constexpr (TPT != 32) __syncthreads();  // `red` is reused by the next token
     }
-    if (TPT == kThreads && MODE == 0 && xc.peers && xc.seq == 0 && threadIdx.x == 0) {
+    if constexpr (XCH) if (xc.seq == 0 && threadIdx.x == 0) {
         uint32_t* stp = xch_step(xc.peers[xc.rank]);
         __threadfence();
         if (atomicAdd(stp + 1, 1u) == gridDim.x * gridDim.y - 1u) {
@@ -1124,6 +1129,18 @@ void launch_token_fused(int nv, dim3 grid, cudaStream_t st, const void* x, const
         if (cap < 2 * sm_count()) cap = 2 * sm_count();
         const int64_t tgrid = groups < cap ? groups : cap;
         if (tpt == 32) KVQ_TFT(32); else if (tpt == 64) KVQ_TFT(64); else KVQ_TFT(128);
+        return;
+    }
+    if (xc.peers) {
+        if constexpr (MODE == 0) {
+#define KVQ_TFX(NV) token_fused_kernel<DT, BITS, NV, 0, kThreads, true><<<grid, kThreads, 0, st>>>((const char*)x, g, eps, (char*)q, scale_out, scale_f32_out, absmax_out, accumulate, tb, xc)
+            if (nv <= 1) KVQ_TFX(1);
+            else if (nv <= 2) KVQ_TFX(2);
+            else if (nv <= 4) KVQ_TFX(4);
+            else if (nv <= 8) KVQ_TFX(8);
+            else KVQ_TFX(0);
+#undef KVQ_TFX
+        }
         return;
     }
     if (nv <= 1) KVQ_TF(1);
