@@ -24,7 +24,8 @@ copy peak) and clock sample:
     c4        : BASELINE configs[3] -- strided / block / budget / prefix+window compaction and chunk-summary
                 pooling at T = 131072, L = 32 x {K, V} in ONE launch each, head-sharded over the N ranks
     decode    : BASELINE configs[4] -- fused dequant decode attention, 80 layers, B8 x 64k, INT8-K/INT4-V,
-                MHA shape and GQA-8, contiguous and paged stores
+                MHA shape and GQA-8, contiguous and paged stores; at N > 1 also the head-sharded decode append
+                (decode.append_sharded: exchange inside the quantize kernel, eager and in a CUDA graph, vs the NCCL form)
     paged     : PagedKVCache append / stitch kernels
     c2        : BASELINE configs[1] (and [0] on the GPU) -- GPT-2 small tok/s through KVCacheBenchmarker.benchmark_method
 --workload picks a subset of the legs (profiling runs); the default runs them all.
@@ -408,9 +409,10 @@ def run_c3(cx: Ctx, cfg, legs):
         bits_halves = [bits[:half], bits[half:]]
 
     def step(timed: bool):
-        # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched), one allreduce in between.  Head-sharded
-        # (N > 1): the batch goes through absmax / quantize in two halves so that the allreduce of one half (NCCL's stream)
-        # overlaps the other half's kernel -- SURVEY 8e: "overlap by launching phase-1 for tensor i+1 before phase-2 of tensor i"
+        # one launch per phase for the whole batch of 64 layer tensors (kvq_*_batched).  Head-sharded (N > 1) the max over ranks of
+        # the 64 absmax words sits between absmax and quantize: by default INSIDE the two kernels (publish / gather over peer-mapped
+        # memory); as A/B a stand-alone exchange kernel (--side-stream-exchange) or NCCL's allreduce (--nccl-absmax), both with the
+        # batch in two halves so that the exchange of one half overlaps the other half's kernel
         n_launch = 3
         if timed:
             e_in = torch.cuda.Event(enable_timing=True)
