@@ -149,3 +149,10 @@ def test_absmax_exchange_single_rank_is_identity():
     ex = AbsmaxExchange(torch.device("cpu"), None)
     b = torch.tensor([3], dtype=torch.int32)
     assert not ex.available and ex.why == "single rank" and ex.exchange_(b) is b
+
+
+def test_shared_exchange_is_none_without_peers():
+    """One process, no process group: the stores' exchange is unavailable ("single rank") and cached; callers take the other path."""
+    from kvq_b200.distributed import shared_exchange
+    assert shared_exchange(torch.device("cpu"), None) is None
+    assert shared_exchange(torch.device("cpu"), None) is None
